@@ -1,0 +1,203 @@
+/* wfstft.h — C ABI of libwfstft.so, the B200 (sm_100a) batched STFT engine that drops in behind
+ * phandasm/waveform's spectrum backend seam.
+ *
+ * What it replaces (paths relative to the reference tree):
+ *   - the pure virtual  WAVSource::tick_spectrum(float)            src/source.hpp:275
+ *     and its three CPU implementations                            src/source_generic.cpp:26-180,
+ *                                                                  src/source_avx.cpp:29-200, src/source_avx2.cpp:24-209
+ *   - the only FFTW calls the plugin makes                         src/source.cpp:1187 (plan), src/source_generic.cpp:106
+ *                                                                  (execute), src/source.cpp:803 (destroy)
+ *   - table construction done in WAVSource::update                 src/source.cpp:1190-1234 (window), :1282-1290 (slope),
+ *                                                                  :898-918 (roll-off), :837-896 (interpolation)
+ *   - the render-time interpolation / smoothing of m_decibels      src/source.cpp:1381-1406, :1510-1546,
+ *                                                                  src/filter.hpp:133-211, src/filter_fma3.cpp:23-219
+ *
+ * Conventions
+ *   - plain C, no exceptions; every function returns WF_OK (0) or a negative wf_status;
+ *     wf_last_error() gives a human-readable reason for the last failure on that engine.
+ *   - one engine handle is externally serialised (the plugin holds m_mtx around tick/render/update,
+ *     src/source.cpp:1326,1348,1079); different handles may be used concurrently from different threads.
+ *   - data pointers in a wf_batch may be HOST or DEVICE pointers (all of one kind per call, detected with
+ *     cudaPointerGetAttributes).  Host buffers are staged through pinned memory inside the call.
+ *   - the engine owns all device memory (tables, per-stream EMA state, staging); the caller owns pcm/out.
+ *   - there is no CPU fallback: without a CUDA device wf_create fails with WF_ERR_NO_DEVICE.
+ */
+#ifndef WFSTFT_H
+#define WFSTFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_ABI_VERSION 1
+
+typedef enum wf_status {
+    WF_OK = 0,
+    WF_ERR_INVALID_ARG = -1,
+    WF_ERR_UNSUPPORTED_FFT_SIZE = -2, /* never a silent approximation: unsupported N is an error */
+    WF_ERR_CUDA = -3,
+    WF_ERR_NO_DEVICE = -4,
+    WF_ERR_OOM = -5,
+    WF_ERR_CAPACITY = -6, /* n_streams > max_streams */
+    WF_ERR_ABI = -7
+} wf_status;
+
+/* Enumerations mirror src/source.hpp:32-93 (same order). */
+typedef enum { WF_WINDOW_NONE, WF_WINDOW_HANN, WF_WINDOW_HAMMING, WF_WINDOW_BLACKMAN, WF_WINDOW_BLACKMAN_HARRIS,
+               WF_WINDOW_POWER_OF_SINE } wf_window;          /* FFTWindow */
+typedef enum { WF_INTERP_POINT, WF_INTERP_LANCZOS, WF_INTERP_CATROM } wf_interp;          /* InterpMode */
+typedef enum { WF_FILTER_NONE, WF_FILTER_GAUSS } wf_filter;                                 /* FilterMode */
+typedef enum { WF_TSMOOTH_NONE, WF_TSMOOTH_EXPONENTIAL, WF_TSMOOTH_TVEXPONENTIAL } wf_tsmooth; /* TSmoothingMode */
+typedef enum { WF_DISPLAY_CURVE, WF_DISPLAY_BAR } wf_display; /* DisplayMode CURVE / BAR+STEPPED_BAR */
+
+/* DSP-relevant subset of the plugin's settings: what WAVSource::get_settings (src/source.cpp:501-674)
+ * leaves in the m_* members that tick_spectrum / init_interp / init_rolloff read.  wf_create applies the
+ * same clamps (fft_size >= 128 and &-16, cutoff and floor/ceiling sanity, :562-577). */
+typedef struct wf_config {
+    uint32_t struct_size;      /* = sizeof(wf_config); ABI check */
+    int32_t device;            /* CUDA device ordinal, -1 = current device */
+    int32_t max_streams;       /* independent sources whose EMA state the engine keeps (>= 1) */
+    uint32_t sample_rate;      /* m_audio_info.samples_per_sec */
+    int32_t capture_channels;  /* m_capture_channels: 1 or 2 (src/source.cpp:1089) */
+    int32_t fft_size;          /* m_fft_size */
+    int32_t window;            /* wf_window, m_window_func */
+    int32_t sine_exponent;     /* m_sine_exponent */
+    int32_t tsmoothing;        /* wf_tsmooth, m_tsmoothing */
+    float gravity;             /* m_gravity */
+    int32_t fast_peaks;        /* m_fast_peaks */
+    float slope;               /* m_slope */
+    float rolloff_q;           /* m_rolloff_q */
+    float rolloff_rate;        /* m_rolloff_rate */
+    int32_t cutoff_low;        /* m_cutoff_low  (Hz) */
+    int32_t cutoff_high;       /* m_cutoff_high (Hz) */
+    int32_t floor_db;          /* m_floor */
+    int32_t ceiling_db;        /* m_ceiling */
+    int32_t stereo;            /* m_stereo (channel_mode == stereo) */
+    int32_t normalize_volume;  /* m_normalize_volume */
+    float volume_target;       /* m_volume_target */
+    float max_gain;            /* m_max_gain */
+    int32_t silence_gate;      /* 1 = reference "wait for gravity" gating, src/source_generic.cpp:63-95 */
+    int32_t display_mode;      /* wf_display */
+    int32_t width;             /* m_width */
+    int32_t bar_width;         /* m_bar_width */
+    int32_t bar_gap;           /* m_bar_gap */
+    int32_t log_scale;         /* m_log_scale */
+    int32_t mirror_freq_axis;  /* m_mirror_freq_axis */
+    int32_t interp_mode;       /* wf_interp, m_interp_mode */
+    int32_t filter_mode;       /* wf_filter, m_filter_mode */
+    float filter_radius;       /* m_filter_radius */
+} wf_config;
+
+/* Facts derived at create time. */
+typedef struct wf_info {
+    int32_t fft_size;         /* after clamping */
+    int32_t bins;             /* fft_size / 2 (Nyquist and above discarded, src/source_avx2.cpp:29) */
+    int32_t capture_channels;
+    int32_t output_channels;  /* m_output_channels, src/source.cpp:1170 */
+    int32_t display_channels; /* m_stereo ? 2 : 1 */
+    int32_t num_points;       /* display points per channel: width (curve) or num_bars (bars) */
+    int32_t num_bars;
+    int32_t interp_taps;      /* 8 (Lanczos a=4), 4 (Catmull-Rom) or 0 (point) */
+    int32_t n_interp_indices;
+    float window_sum;         /* m_window_sum */
+    float db_min;             /* DB_MIN = 20*log10f(FLT_MIN), src/source.cpp:43 */
+    int32_t device;
+    int32_t sm_count;
+} wf_info;
+
+typedef enum wf_table {
+    WF_TABLE_WINDOW = 0,        /* float[fft_size]   m_window_coefficients */
+    WF_TABLE_SLOPE = 1,         /* float[bins]       m_slope_modifiers     */
+    WF_TABLE_ROLLOFF = 2,       /* float[bins]       m_rolloff_modifiers   */
+    WF_TABLE_INTERP_INDICES = 3,/* float[n_interp_indices] m_interp_indices */
+    WF_TABLE_INTERP_WEIGHTS = 4,/* float[n_interp_indices*interp_taps] m_interp_kernel.weights */
+    WF_TABLE_BAND_WIDTHS = 5,   /* int32 stored as float-sized words [num_bars] m_band_widths */
+    WF_TABLE_GAUSS = 6          /* float[2*ceil(3 sigma)-1] m_kernel.weights */
+} wf_table;
+
+/* One call = n_streams independent sources x n_frames consecutive ticks.
+ *   frame t of capture channel c of stream s = pcm[s*stream_stride + c*channel_stride + t*hop ... + fft_size)
+ * i.e. what CircularBuffer::peek_front hands tick_spectrum on successive ticks (src/source_generic.cpp:55-59)
+ * when `hop` new samples arrive per tick.  The EMA recurrence (src/source_generic.cpp:124-132) runs over t
+ * inside the call and continues across calls through the engine's per-stream state. */
+typedef struct wf_batch {
+    uint32_t struct_size;      /* = sizeof(wf_batch) */
+    int32_t n_streams;
+    int32_t n_frames;
+    int32_t hop;               /* samples between consecutive frames (>= 1) */
+    int32_t first_stream;      /* state slot of stream 0 of this batch (0 <= first_stream, first+n <= max_streams) */
+    float seconds;             /* tick delta for TVEXPONENTIAL gravity (src/source.hpp:301-312); ignored otherwise */
+    const float *pcm;          /* planar float PCM, host or device */
+    int64_t stream_stride;     /* in floats */
+    int64_t channel_stride;    /* in floats */
+    const float *input_rms;    /* optional [n_streams][n_frames] m_input_rms per tick (volume normalisation) */
+    const uint8_t *skip_mask;  /* optional [n_streams][n_frames]: nonzero = "not enough audio" for that tick */
+    float *out_db;             /* optional [n_streams][n_frames][display_channels][bins]       m_decibels      */
+    float *out_points;         /* optional [n_streams][n_frames][display_channels][num_points] interpolated dB */
+    uint8_t *out_silent;       /* optional [n_streams][n_frames] m_last_silent after the tick */
+    float *out_peak;           /* optional [n_frames]: max over streams/channels/bins>=1 of the dB output
+                                  (input to the cross-channel peak normalisation; all-reduce(max) it across GPUs) */
+} wf_batch;
+
+typedef struct wf_engine wf_engine;
+
+int wf_abi_version(void);
+const char *wf_strerror(int status);
+const char *wf_last_error(const wf_engine *e);
+
+/* Fill cfg with the plugin's defaults (src/source.cpp:119-174); sets struct_size. */
+void wf_config_init(wf_config *cfg);
+
+/* ≙ callbacks::create + WAVSource::update (src/source.cpp:87-102, 1077-1322): validates settings, builds all
+ * tables, allocates device state.  Unsupported fft_size -> WF_ERR_UNSUPPORTED_FFT_SIZE. */
+int wf_create(const wf_config *cfg, wf_engine **out);
+/* ≙ WAVSource::~WAVSource / free_bufs (src/source.cpp:782-808). */
+void wf_destroy(wf_engine *e);
+
+int wf_get_info(const wf_engine *e, wf_info *info);
+/* Copies a host copy of a table; returns element count (>= 0) or a negative status. out may be NULL. */
+int64_t wf_get_table(const wf_engine *e, int which, float *out, int64_t capacity);
+/* ≙ WAVSource::get_gravity(seconds), src/source.hpp:301-312. */
+float wf_gravity(const wf_engine *e, float seconds);
+
+/* ≙ tick_spectrum for every (stream, tick) of the batch (+ render-time interpolation when out_points is set).
+ * Blocking: returns after results are in the caller's buffers. */
+int wf_process(wf_engine *e, const wf_batch *batch);
+/* Same, enqueued on `cuda_stream` (a cudaStream_t; NULL = the engine's own stream) without synchronising.
+ * With host pointers the copies are enqueued on the same stream (pinned memory recommended). */
+int wf_process_async(wf_engine *e, const wf_batch *batch, void *cuda_stream);
+int wf_synchronize(wf_engine *e);
+
+/* ≙ the timeout / hidden branch (src/source_generic.cpp:36-48): zero EMA state, outputs := DB_MIN,
+ * m_last_silent := true for streams [first, first+count). */
+int wf_reset_state(wf_engine *e, int32_t first_stream, int32_t count);
+
+/* Checkpoint / restore of the per-stream recurrence state (host buffers):
+ *   tsmooth  [count][capture_channels][bins]   m_tsmooth_buf
+ *   hold_db  [count][output_channels][bins]    m_decibels as left by the last tick
+ *   flags    [count]                           bit0 = m_last_silent */
+int wf_get_state(wf_engine *e, int32_t first_stream, int32_t count, float *tsmooth, float *hold_db, uint8_t *flags);
+int wf_set_state(wf_engine *e, int32_t first_stream, int32_t count, const float *tsmooth, const float *hold_db,
+                 const uint8_t *flags);
+
+/* Cross-channel peak normalisation (BASELINE config 5; generalises the single-source volume normalisation of
+ * src/source_generic.cpp:161-167 to a peak shared by all channels on all GPUs):
+ *   gain[t] = min(target_db - peak[t], max_gain);  out[s][t][ch][k] += gain[t]  for k >= 1
+ * `peak` is the (all-reduced) wf_batch.out_peak array; `data` is an out_db-shaped ([..][bins]) or
+ * out_points-shaped ([..][num_points]) buffer, `row_len` its innermost length.  Device or host pointers. */
+int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_frames, int32_t row_len,
+                      const float *peak, float target_db, float max_gain, void *cuda_stream);
+
+/* Number of kernel launches this engine has issued (bench.py reports it as gpu_launches). */
+int64_t wf_launch_count(const wf_engine *e);
+/* Device time (ms) of the kernel section of the most recent wf_process / wf_process_async / wf_peak_normalize call,
+ * measured with CUDA events on the launching stream; < 0 if none. Synchronises on the recorded events. */
+float wf_last_kernel_ms(wf_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFSTFT_H */

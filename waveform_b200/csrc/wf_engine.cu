@@ -1,0 +1,776 @@
+// wf_engine.cu — libwfstft.so: the C ABI of include/wfstft.h on top of the fused sm_100a kernel.
+//
+// Host responsibilities (mirrors what WAVSource owns in the reference, src/source.hpp:95-347):
+//   * settings -> tables (wf_tables.cpp ≙ WAVSource::update), uploaded once per engine
+//   * per-stream recurrence state in device memory (m_tsmooth_buf, m_decibels, m_last_silent)
+//   * staging of host buffers, kernel dispatch by (fft_size, capture_channels), error reporting
+// There is no CPU compute path: if CUDA is unavailable wf_create fails.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "wf_kernels.cuh"
+#include "wf_tables.hpp"
+#include "wfstft.h"
+
+using namespace wf;
+
+struct wf_engine {
+    Tables tab;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::string last_error;
+    int64_t launches = 0;
+
+    // device tables
+    float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
+    float *d_tw = nullptr, *d_tw_post = nullptr;
+    float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
+    int *d_band_widths = nullptr, *d_band_offsets = nullptr;
+    // per-stream state
+    float *d_state = nullptr, *d_hold = nullptr;
+    unsigned char *d_flags = nullptr;
+    // staging for host-pointer batches (grown on demand)
+    float *s_pcm = nullptr, *s_out_db = nullptr, *s_out_points = nullptr, *s_rms = nullptr, *s_peak = nullptr;
+    unsigned char *s_skip = nullptr, *s_silent = nullptr;
+    size_t s_pcm_cap = 0, s_out_db_cap = 0, s_out_points_cap = 0, s_rms_cap = 0, s_peak_cap = 0, s_skip_cap = 0,
+           s_silent_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int set_err(wf_engine *e, int code, const char *fmt, ...)
+{
+    if(e)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        e->last_error = buf;
+    }
+    return code;
+}
+
+#define WF_CUDA(e, call)                                                                                              \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t _err = (call);                                                                                    \
+        if(_err != cudaSuccess)                                                                                       \
+            return set_err((e), (_err == cudaErrorMemoryAllocation) ? WF_ERR_OOM : WF_ERR_CUDA, "%s failed: %s", #call, \
+                           cudaGetErrorString(_err));                                                                 \
+    } while(0)
+
+template<typename T>
+int upload(wf_engine *e, T **dst, const std::vector<T> &src)
+{
+    *dst = nullptr;
+    if(src.empty())
+        return WF_OK;
+    WF_CUDA(e, cudaMalloc((void **)dst, src.size() * sizeof(T)));
+    WF_CUDA(e, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return WF_OK;
+}
+
+template<typename T>
+int ensure(wf_engine *e, T **buf, size_t *cap, size_t need)
+{
+    if(need <= *cap)
+        return WF_OK;
+    if(*buf)
+        cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    WF_CUDA(e, cudaMalloc((void **)buf, need * sizeof(T)));
+    *cap = need;
+    return WF_OK;
+}
+
+bool supported_fft_size(int n)
+{
+    switch(n)
+    {
+    case 128: case 256: case 512: case 1024: case 2048: case 4096: case 8192: case 16384: case 32768: return true;
+    default: return false;
+    }
+}
+
+bool is_device_ptr(const void *p)
+{
+    if(!p)
+        return false;
+    cudaPointerAttributes a{};
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template<int N, int CC>
+int launch_fused(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra_smem)
+{
+    using G = Geo<N>;
+    const size_t smem = (size_t)G::GROUPS * G::BUF * sizeof(float2) + extra_smem;
+    static thread_local size_t configured[8] = {0};
+    int dev = e->device & 7;
+    if(smem > 48 * 1024 && configured[dev] < smem)
+    {
+        WF_CUDA(e, cudaFuncSetAttribute(stft_fused_kernel<N, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    const int grid = (kp.n_streams + G::GROUPS - 1) / G::GROUPS;
+    stft_fused_kernel<N, CC><<<grid, G::CTA, smem, st>>>(kp);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return WF_OK;
+}
+
+template<int CC>
+int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
+{
+    switch(e->tab.N)
+    {
+    case 128: return launch_fused<128, CC>(e, kp, st, extra);
+    case 256: return launch_fused<256, CC>(e, kp, st, extra);
+    case 512: return launch_fused<512, CC>(e, kp, st, extra);
+    case 1024: return launch_fused<1024, CC>(e, kp, st, extra);
+    case 2048: return launch_fused<2048, CC>(e, kp, st, extra);
+    case 4096: return launch_fused<4096, CC>(e, kp, st, extra);
+    case 8192: return launch_fused<8192, CC>(e, kp, st, extra);
+    case 16384: return launch_fused<16384, CC>(e, kp, st, extra);
+    case 32768: return launch_fused<32768, CC>(e, kp, st, extra);
+    default: return set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d has no kernel", e->tab.N);
+    }
+}
+
+int fill_device(wf_engine *e, float *p, long long n, float v, cudaStream_t st)
+{
+    if(n <= 0)
+        return WF_OK;
+    int blocks = (int)std::min<long long>((n + 255) / 256, 1184);
+    fill_kernel<<<blocks, 256, 0, st>>>(p, n, v);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return WF_OK;
+}
+
+int init_state(wf_engine *e, int first, int count, bool reset_semantics, cudaStream_t st)
+{
+    const Tables &t = e->tab;
+    const int cc = t.cfg.capture_channels, och = t.output_channels, B = t.B;
+    WF_CUDA(e, cudaMemsetAsync(e->d_state + (size_t)first * cc * B, 0, (size_t)count * cc * B * sizeof(float), st));
+    if(reset_semantics && och > t.display_channels)
+    {
+        // the timeout branch only refills the DISPLAY channels with DB_MIN (src/source_generic.cpp:43-45);
+        // slot 1 of a 2ch->mono mix keeps its last linear magnitudes.
+        for(int s = first; s < first + count; ++s)
+        {
+            int rc = fill_device(e, e->d_hold + (size_t)s * och * B, (long long)t.display_channels * B, t.db_min, st);
+            if(rc)
+                return rc;
+        }
+    }
+    else
+    {
+        int rc = fill_device(e, e->d_hold + (size_t)first * och * B, (long long)count * och * B, t.db_min, st);
+        if(rc)
+            return rc;
+    }
+    // flags: bit0 last_silent; bit1/2: previous outputs all <= floor-10 (DB_MIN is)
+    const bool below = !(t.db_min > (float)(t.cfg.floor_db - 10));
+    const unsigned char fl = (unsigned char)((reset_semantics ? 1u : 0u) | (below ? 6u : 0u));
+    WF_CUDA(e, cudaMemsetAsync(e->d_flags + first, fl, (size_t)count, st));
+    return WF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int wf_abi_version(void) { return WF_ABI_VERSION; }
+
+const char *wf_strerror(int status)
+{
+    switch(status)
+    {
+    case WF_OK: return "ok";
+    case WF_ERR_INVALID_ARG: return "invalid argument";
+    case WF_ERR_UNSUPPORTED_FFT_SIZE: return "unsupported fft_size (supported: powers of two 128..32768)";
+    case WF_ERR_CUDA: return "CUDA error";
+    case WF_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU fallback)";
+    case WF_ERR_OOM: return "out of device memory";
+    case WF_ERR_CAPACITY: return "stream range exceeds max_streams";
+    case WF_ERR_ABI: return "struct_size mismatch (ABI)";
+    default: return "unknown status";
+    }
+}
+
+const char *wf_last_error(const wf_engine *e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+void wf_config_init(wf_config *c)
+{
+    // plugin defaults, src/source.cpp:119-174
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (uint32_t)sizeof(wf_config);
+    c->device = -1;
+    c->max_streams = 1;
+    c->sample_rate = 48000;
+    c->capture_channels = 2;
+    c->fft_size = 4096;
+    c->window = WF_WINDOW_HANN;
+    c->sine_exponent = 2;
+    c->tsmoothing = WF_TSMOOTH_EXPONENTIAL;
+    c->gravity = 0.65f;
+    c->fast_peaks = 0;
+    c->slope = 0.0f;
+    c->rolloff_q = 0.0f;
+    c->rolloff_rate = 0.0f;
+    c->cutoff_low = 30;
+    c->cutoff_high = 17500;
+    c->floor_db = -65;
+    c->ceiling_db = 0;
+    c->stereo = 0;
+    c->normalize_volume = 0;
+    c->volume_target = -8.0f;
+    c->max_gain = 30.0f;
+    c->silence_gate = 1;
+    c->display_mode = WF_DISPLAY_CURVE;
+    c->width = 800;
+    c->bar_width = 24;
+    c->bar_gap = 6;
+    c->log_scale = 1;
+    c->mirror_freq_axis = 0;
+    c->interp_mode = WF_INTERP_CATROM;
+    c->filter_mode = WF_FILTER_NONE;
+    c->filter_radius = 1.5f;
+}
+
+int wf_create(const wf_config *cfg, wf_engine **out)
+{
+    if(!cfg || !out)
+        return WF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if(cfg->struct_size != sizeof(wf_config))
+        return WF_ERR_ABI;
+    wf_engine *e = new(std::nothrow) wf_engine();
+    if(!e)
+        return WF_ERR_OOM;
+    auto bail = [&](int code) {
+        g_create_error = e->last_error; // readable through wf_last_error(NULL) after the engine is gone
+        wf_destroy(e);
+        return code;
+    };
+
+    const char *why = nullptr;
+    int rc = build_tables(*cfg, e->tab, &why);
+    if(rc != WF_OK)
+    {
+        set_err(e, rc, "%s", why ? why : "bad config");
+        return bail(rc);
+    }
+    if(!supported_fft_size(e->tab.N))
+        return bail(set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d unsupported", e->tab.N));
+
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return bail(set_err(e, WF_ERR_NO_DEVICE, "no CUDA device"));
+    }
+    int dev = cfg->device;
+    if(dev < 0)
+    {
+        if(cudaGetDevice(&dev) != cudaSuccess)
+            return bail(set_err(e, WF_ERR_CUDA, "cudaGetDevice failed"));
+    }
+    if(dev >= ndev)
+        return bail(set_err(e, WF_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, ndev));
+    e->device = dev;
+
+#define WF_TRY(x)                 \
+    do                            \
+    {                             \
+        int _rc = (x);            \
+        if(_rc != WF_OK)          \
+            return bail(_rc);     \
+    } while(0)
+#define WF_CUDA_C(call)                                                                                      \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t _err = (call);                                                                           \
+        if(_err != cudaSuccess)                                                                              \
+            return bail(set_err(e, (_err == cudaErrorMemoryAllocation) ? WF_ERR_OOM : WF_ERR_CUDA, "%s: %s", \
+                                #call, cudaGetErrorString(_err)));                                           \
+    } while(0)
+
+    WF_CUDA_C(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    WF_CUDA_C(cudaGetDeviceProperties(&prop, dev));
+    e->sm_count = prop.multiProcessorCount;
+    if(prop.major < 10)
+        return bail(set_err(e, WF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                            prop.major, prop.minor));
+    WF_CUDA_C(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    WF_CUDA_C(cudaEventCreate(&e->ev0));
+    WF_CUDA_C(cudaEventCreate(&e->ev1));
+
+    const Tables &t = e->tab;
+    WF_TRY(upload(e, &e->d_window, t.window));
+    WF_TRY(upload(e, &e->d_slope, t.slope));
+    WF_TRY(upload(e, &e->d_rolloff, t.rolloff));
+    WF_TRY(upload(e, &e->d_tw, t.tw));
+    WF_TRY(upload(e, &e->d_tw_post, t.tw_post));
+    WF_TRY(upload(e, &e->d_interp_idx, t.interp_indices));
+    WF_TRY(upload(e, &e->d_interp_w, t.interp_weights));
+    WF_TRY(upload(e, &e->d_gauss, t.gauss));
+    WF_TRY(upload(e, &e->d_band_widths, t.band_widths));
+    WF_TRY(upload(e, &e->d_band_offsets, t.band_offsets));
+
+    const size_t S = (size_t)t.cfg.max_streams;
+    WF_CUDA_C(cudaMalloc((void **)&e->d_state, S * t.cfg.capture_channels * t.B * sizeof(float)));
+    WF_CUDA_C(cudaMalloc((void **)&e->d_hold, S * t.output_channels * t.B * sizeof(float)));
+    WF_CUDA_C(cudaMalloc((void **)&e->d_flags, S));
+    WF_TRY(init_state(e, 0, (int)S, false, e->stream));
+    WF_CUDA_C(cudaStreamSynchronize(e->stream));
+#undef WF_TRY
+#undef WF_CUDA_C
+    *out = e;
+    return WF_OK;
+}
+
+void wf_destroy(wf_engine *e)
+{
+    if(!e)
+        return;
+    if(e->stream)
+    {
+        cudaSetDevice(e->device);
+        cudaStreamSynchronize(e->stream);
+    }
+    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_interp_idx, e->d_interp_w,
+                    e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
+                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent};
+    for(void *p : ptrs)
+        if(p)
+            cudaFree(p);
+    if(e->ev0)
+        cudaEventDestroy(e->ev0);
+    if(e->ev1)
+        cudaEventDestroy(e->ev1);
+    if(e->stream)
+        cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int wf_get_info(const wf_engine *e, wf_info *info)
+{
+    if(!e || !info)
+        return WF_ERR_INVALID_ARG;
+    const Tables &t = e->tab;
+    info->fft_size = t.N;
+    info->bins = t.B;
+    info->capture_channels = t.cfg.capture_channels;
+    info->output_channels = t.output_channels;
+    info->display_channels = t.display_channels;
+    info->num_points = t.num_points;
+    info->num_bars = t.num_bars;
+    info->interp_taps = t.interp_taps;
+    info->n_interp_indices = (int32_t)t.interp_indices.size();
+    info->window_sum = t.window_sum;
+    info->db_min = t.db_min;
+    info->device = e->device;
+    info->sm_count = e->sm_count;
+    return WF_OK;
+}
+
+int64_t wf_get_table(const wf_engine *e, int which, float *out, int64_t capacity)
+{
+    if(!e)
+        return WF_ERR_INVALID_ARG;
+    const Tables &t = e->tab;
+    const void *src = nullptr;
+    int64_t n = 0;
+    switch(which)
+    {
+    case WF_TABLE_WINDOW: src = t.window.data(); n = (int64_t)t.window.size(); break;
+    case WF_TABLE_SLOPE: src = t.slope.data(); n = (int64_t)t.slope.size(); break;
+    case WF_TABLE_ROLLOFF: src = t.rolloff.data(); n = (int64_t)t.rolloff.size(); break;
+    case WF_TABLE_INTERP_INDICES: src = t.interp_indices.data(); n = (int64_t)t.interp_indices.size(); break;
+    case WF_TABLE_INTERP_WEIGHTS: src = t.interp_weights.data(); n = (int64_t)t.interp_weights.size(); break;
+    case WF_TABLE_BAND_WIDTHS: src = t.band_widths.data(); n = (int64_t)t.band_widths.size(); break;
+    case WF_TABLE_GAUSS: src = t.gauss.data(); n = (int64_t)t.gauss.size(); break;
+    default: return WF_ERR_INVALID_ARG;
+    }
+    if(out && n > 0)
+    {
+        if(capacity < n)
+            return WF_ERR_INVALID_ARG;
+        memcpy(out, src, (size_t)n * 4);
+    }
+    return n;
+}
+
+float wf_gravity(const wf_engine *e, float seconds) { return e ? gravity_for(e->tab.cfg, seconds) : 0.0f; }
+
+int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
+{
+    if(!e || !b)
+        return WF_ERR_INVALID_ARG;
+    if(b->struct_size != sizeof(wf_batch))
+        return set_err(e, WF_ERR_ABI, "wf_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_batch));
+    const Tables &t = e->tab;
+    const int cc = t.cfg.capture_channels, dch = t.display_channels, och = t.output_channels, B = t.B, N = t.N;
+    if(b->n_streams < 0 || b->n_frames < 0 || b->hop < 1)
+        return set_err(e, WF_ERR_INVALID_ARG, "n_streams/n_frames must be >= 0 and hop >= 1");
+    if(b->first_stream < 0 || (int64_t)b->first_stream + b->n_streams > t.cfg.max_streams)
+        return set_err(e, WF_ERR_CAPACITY, "streams [%d, %d) exceed max_streams %d", b->first_stream,
+                       b->first_stream + b->n_streams, t.cfg.max_streams);
+    if(b->n_streams == 0 || b->n_frames == 0)
+        return WF_OK;
+    if(!b->pcm)
+        return set_err(e, WF_ERR_INVALID_ARG, "pcm is null");
+    if(b->stream_stride < 0 || b->channel_stride < 0)
+        return set_err(e, WF_ERR_INVALID_ARG, "negative strides are not supported");
+    if(b->out_points && t.num_points <= 0)
+        return set_err(e, WF_ERR_INVALID_ARG, "out_points requested but the engine has no display points");
+
+    WF_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    const bool dev_ptrs = is_device_ptr(b->pcm);
+    const size_t S = (size_t)b->n_streams, T = (size_t)b->n_frames;
+
+    KParams kp{};
+    const float *pcm = b->pcm;
+    float *out_db = b->out_db, *out_points = b->out_points, *out_peak = b->out_peak;
+    const float *rms = b->input_rms;
+    const unsigned char *skip = b->skip_mask;
+    unsigned char *silent = b->out_silent;
+    const size_t span = (S - 1) * (size_t)b->stream_stride + (size_t)(cc - 1) * (size_t)b->channel_stride +
+                        (T - 1) * (size_t)b->hop + (size_t)N;
+    if(!dev_ptrs)
+    {
+        int rc;
+        if((rc = ensure(e, &e->s_pcm, &e->s_pcm_cap, span)))
+            return rc;
+        WF_CUDA(e, cudaMemcpyAsync(e->s_pcm, b->pcm, span * sizeof(float), cudaMemcpyHostToDevice, st));
+        pcm = e->s_pcm;
+        if(b->out_db)
+        {
+            if((rc = ensure(e, &e->s_out_db, &e->s_out_db_cap, S * T * dch * B)))
+                return rc;
+            out_db = e->s_out_db;
+        }
+        if(b->out_points)
+        {
+            if((rc = ensure(e, &e->s_out_points, &e->s_out_points_cap, S * T * dch * t.num_points)))
+                return rc;
+            out_points = e->s_out_points;
+        }
+        if(b->input_rms)
+        {
+            if((rc = ensure(e, &e->s_rms, &e->s_rms_cap, S * T)))
+                return rc;
+            WF_CUDA(e, cudaMemcpyAsync(e->s_rms, b->input_rms, S * T * sizeof(float), cudaMemcpyHostToDevice, st));
+            rms = e->s_rms;
+        }
+        if(b->skip_mask)
+        {
+            if((rc = ensure(e, &e->s_skip, &e->s_skip_cap, S * T)))
+                return rc;
+            WF_CUDA(e, cudaMemcpyAsync(e->s_skip, b->skip_mask, S * T, cudaMemcpyHostToDevice, st));
+            skip = e->s_skip;
+        }
+        if(b->out_silent)
+        {
+            if((rc = ensure(e, &e->s_silent, &e->s_silent_cap, S * T)))
+                return rc;
+            silent = e->s_silent;
+        }
+        if(b->out_peak)
+        {
+            if((rc = ensure(e, &e->s_peak, &e->s_peak_cap, T)))
+                return rc;
+            out_peak = e->s_peak;
+        }
+    }
+
+    kp.pcm = pcm;
+    kp.stream_stride = b->stream_stride;
+    kp.channel_stride = b->channel_stride;
+    kp.n_streams = b->n_streams;
+    kp.n_frames = b->n_frames;
+    kp.hop = b->hop;
+    kp.aligned8 = (((uintptr_t)pcm & 7u) == 0) && ((b->stream_stride & 1) == 0) && ((b->channel_stride & 1) == 0) &&
+                  ((b->hop & 1) == 0);
+    kp.input_rms = rms;
+    kp.skip_mask = skip;
+    kp.window = e->d_window;
+    kp.window2 = reinterpret_cast<const float2 *>(e->d_window);
+    kp.tw = reinterpret_cast<const float2 *>(e->d_tw);
+    kp.tw_post = reinterpret_cast<const float2 *>(e->d_tw_post);
+    kp.slope = e->d_slope;
+    kp.rolloff = e->d_rolloff;
+    kp.state = e->d_state + (size_t)b->first_stream * cc * B;
+    kp.hold_db = e->d_hold + (size_t)b->first_stream * och * B;
+    kp.flags = e->d_flags + b->first_stream;
+    kp.out_db = out_db;
+    kp.out_points = out_points;
+    kp.out_silent = silent;
+    kp.out_peak = out_peak;
+    kp.coef_half = (2.0f / t.window_sum) * 0.5f; // mag_coefficient/2: the split pass leaves 2*X (src/source_generic.cpp:110)
+    kp.g = (t.cfg.tsmoothing == WF_TSMOOTH_NONE) ? 0.0f : gravity_for(t.cfg, b->seconds);
+    kp.g2 = 1.0f - kp.g;
+    kp.tsmooth = t.cfg.tsmoothing != WF_TSMOOTH_NONE;
+    kp.fast_peaks = t.cfg.fast_peaks;
+    kp.stereo = t.cfg.stereo;
+    kp.och = och;
+    kp.dch = dch;
+    kp.gate = t.cfg.silence_gate;
+    kp.floor_m10 = (float)(t.cfg.floor_db - 10);
+    kp.db_min = t.db_min;
+    kp.normalize = t.cfg.normalize_volume;
+    kp.vol_target = t.cfg.volume_target;
+    kp.max_gain = t.cfg.max_gain;
+    kp.write_hold = 1;
+    kp.interp_idx = e->d_interp_idx;
+    kp.interp_w = e->d_interp_w;
+    kp.band_widths = e->d_band_widths;
+    kp.band_offsets = e->d_band_offsets;
+    kp.n_points = t.num_points;
+    kp.taps = t.interp_taps;
+    kp.radius = t.interp_radius;
+    kp.display_bar = (t.cfg.display_mode == WF_DISPLAY_BAR);
+    kp.interp_mode = t.cfg.interp_mode;
+    kp.gauss_w = e->d_gauss;
+    kp.gauss_radius = t.gauss_radius;
+    kp.gauss_size = (int)t.gauss.size();
+    kp.gauss_sum = t.gauss_sum;
+    kp.filter = (t.cfg.filter_mode == WF_FILTER_GAUSS);
+
+    WF_CUDA(e, cudaEventRecord(e->ev0, st));
+    if(out_peak)
+    {
+        int rc = fill_device(e, out_peak, (long long)T, -INFINITY, st);
+        if(rc)
+            return rc;
+    }
+    // shared memory for the gaussian intermediate: [groups][2][num_points] floats
+    size_t extra = 0;
+    if(out_points && kp.filter)
+    {
+        int groups = 1;
+        switch(N)
+        {
+        case 128: groups = Geo<128>::GROUPS; break;
+        case 256: groups = Geo<256>::GROUPS; break;
+        case 512: groups = Geo<512>::GROUPS; break;
+        case 1024: groups = Geo<1024>::GROUPS; break;
+        case 2048: groups = Geo<2048>::GROUPS; break;
+        default: groups = 1; break;
+        }
+        extra = (size_t)groups * 2 * (size_t)t.num_points * sizeof(float);
+    }
+    int rc = (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
+    if(rc)
+        return rc;
+    WF_CUDA(e, cudaEventRecord(e->ev1, st));
+    e->ev_valid = true;
+
+    if(!dev_ptrs)
+    {
+        if(b->out_db)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_db, out_db, S * T * dch * B * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if(b->out_points)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_points, out_points, S * T * dch * t.num_points * sizeof(float),
+                                       cudaMemcpyDeviceToHost, st));
+        if(b->out_silent)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_silent, silent, S * T, cudaMemcpyDeviceToHost, st));
+        if(b->out_peak)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_peak, out_peak, T * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    return WF_OK;
+}
+
+int wf_process(wf_engine *e, const wf_batch *b)
+{
+    int rc = wf_process_async(e, b, nullptr);
+    if(rc)
+        return rc;
+    WF_CUDA(e, cudaStreamSynchronize(e->stream));
+    return WF_OK;
+}
+
+int wf_synchronize(wf_engine *e)
+{
+    if(!e)
+        return WF_ERR_INVALID_ARG;
+    WF_CUDA(e, cudaSetDevice(e->device));
+    WF_CUDA(e, cudaStreamSynchronize(e->stream));
+    return WF_OK;
+}
+
+int wf_reset_state(wf_engine *e, int32_t first, int32_t count)
+{
+    if(!e)
+        return WF_ERR_INVALID_ARG;
+    if(first < 0 || count < 0 || (int64_t)first + count > e->tab.cfg.max_streams)
+        return set_err(e, WF_ERR_CAPACITY, "reset range out of bounds");
+    if(count == 0)
+        return WF_OK;
+    WF_CUDA(e, cudaSetDevice(e->device));
+    int rc = init_state(e, first, count, true, e->stream);
+    if(rc)
+        return rc;
+    WF_CUDA(e, cudaStreamSynchronize(e->stream));
+    return WF_OK;
+}
+
+int wf_get_state(wf_engine *e, int32_t first, int32_t count, float *tsmooth, float *hold_db, uint8_t *flags)
+{
+    if(!e)
+        return WF_ERR_INVALID_ARG;
+    const Tables &t = e->tab;
+    if(first < 0 || count < 0 || (int64_t)first + count > t.cfg.max_streams)
+        return set_err(e, WF_ERR_CAPACITY, "state range out of bounds");
+    WF_CUDA(e, cudaSetDevice(e->device));
+    WF_CUDA(e, cudaStreamSynchronize(e->stream));
+    const size_t cc = (size_t)t.cfg.capture_channels, och = (size_t)t.output_channels, B = (size_t)t.B;
+    if(tsmooth)
+        WF_CUDA(e, cudaMemcpy(tsmooth, e->d_state + first * cc * B, count * cc * B * sizeof(float), cudaMemcpyDeviceToHost));
+    if(hold_db)
+        WF_CUDA(e, cudaMemcpy(hold_db, e->d_hold + first * och * B, count * och * B * sizeof(float), cudaMemcpyDeviceToHost));
+    if(flags)
+    {
+        WF_CUDA(e, cudaMemcpy(flags, e->d_flags + first, (size_t)count, cudaMemcpyDeviceToHost));
+        for(int i = 0; i < count; ++i)
+            flags[i] &= 1u;
+    }
+    return WF_OK;
+}
+
+int wf_set_state(wf_engine *e, int32_t first, int32_t count, const float *tsmooth, const float *hold_db,
+                 const uint8_t *flags)
+{
+    if(!e)
+        return WF_ERR_INVALID_ARG;
+    const Tables &t = e->tab;
+    if(first < 0 || count < 0 || (int64_t)first + count > t.cfg.max_streams)
+        return set_err(e, WF_ERR_CAPACITY, "state range out of bounds");
+    WF_CUDA(e, cudaSetDevice(e->device));
+    WF_CUDA(e, cudaStreamSynchronize(e->stream));
+    const size_t cc = (size_t)t.cfg.capture_channels, och = (size_t)t.output_channels, B = (size_t)t.B;
+    if(tsmooth)
+        WF_CUDA(e, cudaMemcpy(e->d_state + first * cc * B, tsmooth, count * cc * B * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<unsigned char> fl((size_t)count);
+    WF_CUDA(e, cudaMemcpy(fl.data(), e->d_flags + first, (size_t)count, cudaMemcpyDeviceToHost));
+    if(hold_db)
+    {
+        WF_CUDA(e, cudaMemcpy(e->d_hold + first * och * B, hold_db, count * och * B * sizeof(float), cudaMemcpyHostToDevice));
+        const float thr = (float)(t.cfg.floor_db - 10);
+        for(int s = 0; s < count; ++s)
+        {
+            unsigned char bits = 0;
+            for(int d = 0; d < t.display_channels; ++d)
+            {
+                bool all_below = true;
+                const float *row = hold_db + ((size_t)s * och + d) * B;
+                for(size_t k = 0; k < B; ++k)
+                    if(row[k] > thr)
+                    {
+                        all_below = false;
+                        break;
+                    }
+                if(all_below)
+                    bits |= (unsigned char)(2u << d);
+            }
+            if(t.display_channels == 1)
+                bits |= 4u;
+            fl[s] = (unsigned char)((fl[s] & 1u) | bits);
+        }
+    }
+    if(flags)
+        for(int s = 0; s < count; ++s)
+            fl[s] = (unsigned char)((fl[s] & ~1u) | (flags[s] & 1u));
+    WF_CUDA(e, cudaMemcpy(e->d_flags + first, fl.data(), (size_t)count, cudaMemcpyHostToDevice));
+    return WF_OK;
+}
+
+int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_frames, int32_t row_len,
+                      const float *peak, float target_db, float max_gain, void *cuda_stream)
+{
+    if(!e || !data || !peak || n_streams < 0 || n_frames < 0 || row_len < 1)
+        return e ? set_err(e, WF_ERR_INVALID_ARG, "bad peak_normalize arguments") : WF_ERR_INVALID_ARG;
+    if(n_streams == 0 || n_frames == 0)
+        return WF_OK;
+    WF_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    const int rows_per_frame = e->tab.display_channels;
+    const size_t total = (size_t)n_streams * n_frames * rows_per_frame * row_len;
+    const bool dev = is_device_ptr(data);
+    float *d_data = data;
+    const float *d_peak = peak;
+    if(!dev)
+    {
+        int rc;
+        if((rc = ensure(e, &e->s_out_db, &e->s_out_db_cap, total)))
+            return rc;
+        if((rc = ensure(e, &e->s_peak, &e->s_peak_cap, (size_t)n_frames)))
+            return rc;
+        WF_CUDA(e, cudaMemcpyAsync(e->s_out_db, data, total * sizeof(float), cudaMemcpyHostToDevice, st));
+        WF_CUDA(e, cudaMemcpyAsync(e->s_peak, peak, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_data = e->s_out_db;
+        d_peak = e->s_peak;
+    }
+    else if(!is_device_ptr(peak))
+    {
+        int rc;
+        if((rc = ensure(e, &e->s_peak, &e->s_peak_cap, (size_t)n_frames)))
+            return rc;
+        WF_CUDA(e, cudaMemcpyAsync(e->s_peak, peak, (size_t)n_frames * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_peak = e->s_peak;
+    }
+    WF_CUDA(e, cudaEventRecord(e->ev0, st));
+    const long long rows = (long long)n_streams * n_frames * rows_per_frame;
+    const int grid = (int)std::min<long long>(rows, (long long)e->sm_count * 16);
+    peak_normalize_kernel<<<grid, 256, 0, st>>>(d_data, n_streams, n_frames, rows_per_frame, row_len, d_peak, target_db,
+                                                max_gain);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    WF_CUDA(e, cudaEventRecord(e->ev1, st));
+    e->ev_valid = true;
+    if(!dev)
+    {
+        WF_CUDA(e, cudaMemcpyAsync(data, d_data, total * sizeof(float), cudaMemcpyDeviceToHost, st));
+        WF_CUDA(e, cudaStreamSynchronize(st));
+    }
+    return WF_OK;
+}
+
+int64_t wf_launch_count(const wf_engine *e) { return e ? e->launches : 0; }
+
+float wf_last_kernel_ms(wf_engine *e)
+{
+    if(!e || !e->ev_valid)
+        return -1.0f;
+    if(cudaEventSynchronize(e->ev1) != cudaSuccess)
+        return -1.0f;
+    float ms = -1.0f;
+    if(cudaEventElapsedTime(&ms, e->ev0, e->ev1) != cudaSuccess)
+        return -1.0f;
+    return ms;
+}
+
+} // extern "C"

@@ -1,0 +1,673 @@
+// wf_kernels.cuh — the fused per-frame spectrum pipeline as ONE sm_100a kernel:
+//
+//   PCM frame (HBM, read once) -> window multiply in the load prologue -> real-to-complex FFT as a
+//   Stockham autosort FFT of the N/2 packed complex points (register radix-8/16/32 butterflies,
+//   one padded shared-memory exchange per pass) -> split (hc2c) pass -> |X|·2/Σw -> slope ->
+//   temporal EMA (state in registers across the frames of a stream) -> dBFS -> volume normalisation
+//   -> roll-off -> coalesced store (HBM, written once) [-> log-frequency interpolation to curve /
+//   bars -> Gaussian smoothing, from the dB spectrum kept in shared memory].
+//
+// Reference semantics restated here: WAVSourceGeneric::tick_spectrum src/source_generic.cpp:26-180,
+// render-time interpolation src/source.cpp:1381-1406,1510-1546 + src/filter.hpp:133-211.
+//
+// Work decomposition: a GROUP of TN threads owns one stream (one WAVSource worth of state) and walks
+// its n_frames ticks in order, because the EMA (src/source_generic.cpp:124-132) and the silence gate
+// (:63-95) are recurrences over ticks.  Streams are independent -> grid = streams / groups-per-CTA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "wf_fft.cuh"
+
+namespace wf {
+
+struct KParams {
+    // input
+    const float *pcm;
+    long long stream_stride, channel_stride;
+    int n_streams, n_frames, hop;
+    int aligned8; // every frame start is 8-byte aligned -> float2 loads
+    const float *input_rms;          // [n_streams][n_frames] or null
+    const unsigned char *skip_mask;  // [n_streams][n_frames] or null
+    // tables
+    const float2 *window2; // window as float2[N/2] or null
+    const float *window;   // same table, scalar view
+    const float2 *tw;      // W_M^k
+    const float2 *tw_post; // W_N^k, k < M
+    const float *slope;    // or null
+    const float *rolloff;  // or null
+    // per-stream persistent state (already offset by first_stream)
+    float *state;          // [streams][CC][B]   m_tsmooth_buf / last linear magnitude
+    float *hold_db;        // [streams][OCH][B]  m_decibels as left by the last tick
+    unsigned char *flags;  // [streams] bit0 last_silent, bit1/2 prev outputs of display slot 0/1 all <= floor-10
+    // outputs
+    float *out_db;             // [streams][frames][DCH][B] or null
+    float *out_points;         // [streams][frames][DCH][n_points] or null
+    unsigned char *out_silent; // [streams][frames] or null
+    float *out_peak;           // [frames] or null (atomic max)
+    // scalars
+    float coef_half;  // (2 / window_sum) / 2
+    float g, g2;      // gravity, 1 - gravity
+    int tsmooth;      // != 0: EMA enabled
+    int fast_peaks;
+    int stereo, och, dch;
+    int gate;
+    float floor_m10;  // (float)(floor - 10)
+    float db_min;
+    int normalize;
+    float vol_target, max_gain;
+    int write_hold;   // write final m_decibels mirror to hold_db at the end of the call
+    // interpolation
+    const float *interp_idx;
+    const float *interp_w;
+    const int *band_widths;
+    const int *band_offsets;
+    int n_points, taps, radius, display_bar, interp_mode;
+    const float *gauss_w;
+    int gauss_radius, gauss_size;
+    float gauss_sum;
+    int filter;
+};
+
+// ---- plans: threads per frame (TN) and per-pass radices for each supported N -----------------------
+template<int TN_, int... Rs>
+struct PlanT {
+    using type = PlanT<TN_, Rs...>;
+    static constexpr int TN = TN_;
+    static constexpr int NPASS = sizeof...(Rs);
+};
+template<int N> struct Plan;
+template<> struct Plan<128> : PlanT<8, 8, 8> {};
+template<> struct Plan<256> : PlanT<8, 16, 8> {};
+template<> struct Plan<512> : PlanT<16, 16, 16> {};
+template<> struct Plan<1024> : PlanT<16, 32, 16> {};
+template<> struct Plan<2048> : PlanT<32, 32, 32> {};
+template<> struct Plan<4096> : PlanT<128, 16, 16, 8> {};
+template<> struct Plan<8192> : PlanT<256, 16, 16, 16> {};
+template<> struct Plan<16384> : PlanT<256, 32, 16, 16> {};
+template<> struct Plan<32768> : PlanT<512, 32, 32, 16> {};
+
+template<int N>
+struct Geo {
+    static constexpr int M = N / 2;
+    static constexpr int TN = Plan<N>::TN;
+    static constexpr int P = M / TN;                          // complex points (= bins) per thread
+    static constexpr int CTA = (TN >= 128) ? TN : 128;        // threads per CTA
+    static constexpr int GROUPS = CTA / TN;                   // streams per CTA
+    static constexpr int BUF = M + (M >> 5);                  // padded exchange buffer, float2 elements
+};
+
+__device__ __forceinline__ int phys(int i) { return i + (i >> 5); }
+
+// ---- group-level sync / votes -----------------------------------------------------------------------
+template<int TN>
+__device__ __forceinline__ void group_sync()
+{
+    if constexpr(TN <= 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+template<int TN>
+__device__ __forceinline__ bool group_any(bool x)
+{
+    if constexpr(TN == 32)
+        return __any_sync(0xffffffffu, x);
+    else if constexpr(TN < 32)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned mask = ((1u << TN) - 1u) << (lane & ~(unsigned)(TN - 1));
+        return (__ballot_sync(0xffffffffu, x) & mask) != 0u;
+    }
+    else
+        return __syncthreads_or(x) != 0;
+}
+template<int TN>
+__device__ __forceinline__ bool group_all(bool x)
+{
+    return !group_any<TN>(!x);
+}
+template<int TN>
+__device__ __forceinline__ float group_max(float x, float *scratch)
+{
+    if constexpr(TN <= 32)
+    {
+#pragma unroll
+        for(int o = TN / 2; o > 0; o >>= 1)
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+        return x;
+    }
+    else
+    {
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1)
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+        __syncthreads();
+        if((threadIdx.x & 31) == 0)
+            scratch[threadIdx.x >> 5] = x;
+        __syncthreads();
+        float m = scratch[0];
+        for(int w = 1; w < TN / 32; ++w)
+            m = fmaxf(m, scratch[w]);
+        return m;
+    }
+}
+
+__device__ __forceinline__ float2 ldg_stream_f2(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float *p, float v)
+{
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// atomic max on a float that may be negative (peak[t] initialised to -inf)
+__device__ __forceinline__ void atomic_max_float(float *addr, float v)
+{
+    if(v >= 0.0f)
+        atomicMax((int *)addr, __float_as_int(v));
+    else
+        atomicMin((unsigned int *)addr, __float_as_uint(v));
+}
+
+// dbfs, src/source.hpp:293-299
+__device__ __forceinline__ float dbfs(float mag, float db_min)
+{
+    return (mag > 0.0f) ? 20.0f * log10f(mag) : db_min;
+}
+
+// ---- Stockham passes -------------------------------------------------------------------------------
+// Pass with radix R, NS = product of previous radices.  v holds P = (M/R/TN)*R points: v[b*R + t].
+template<int M, int TN, int R, int NS, bool FIRST>
+struct Pass {
+    static constexpr int BF = M / R;     // butterflies in this pass
+    static constexpr int BPT = BF / TN;  // butterflies per thread
+    static_assert(BPT >= 1 && BPT * TN == BF, "plan does not tile");
+
+    template<int PP>
+    static __device__ __forceinline__ void load_smem(float2 (&v)[PP], const float2 *buf, int tid)
+    {
+#pragma unroll
+        for(int b = 0; b < BPT; ++b)
+#pragma unroll
+            for(int t = 0; t < R; ++t)
+                v[b * R + t] = buf[phys(tid + b * TN + t * BF)];
+    }
+
+    // twiddle (for NS > 1), DFT-R, store in Stockham order
+    template<int PP>
+    static __device__ __forceinline__ void compute_store(float2 (&v)[PP], float2 *buf, const float2 *__restrict__ tw,
+                                                         int tid)
+    {
+#pragma unroll
+        for(int b = 0; b < BPT; ++b)
+        {
+            const int j = tid + b * TN;
+            float2 x[R];
+#pragma unroll
+            for(int t = 0; t < R; ++t)
+                x[t] = v[b * R + t];
+            if constexpr(NS > 1)
+            {
+                const int jm = j & (NS - 1);
+                constexpr int STEP = M / (NS * R);
+#pragma unroll
+                for(int t = 1; t < R; ++t)
+                    x[t] = cmul(x[t], __ldg(&tw[jm * t * STEP]));
+            }
+            dft_bitrev<R>(x);
+            const int base = (j / NS) * (NS * R) + (j & (NS - 1));
+#pragma unroll
+            for(int t = 0; t < R; ++t)
+                buf[phys(base + t * NS)] = x[bitrev<R>(t)];
+        }
+    }
+};
+
+template<int M, int TN, int NS, int... Rs>
+struct LaterPasses;
+template<int M, int TN, int NS>
+struct LaterPasses<M, TN, NS> {
+    template<int PP>
+    static __device__ __forceinline__ void run(float2 (&)[PP], float2 *, const float2 *, int) {}
+};
+template<int M, int TN, int NS, int R, int... Rest>
+struct LaterPasses<M, TN, NS, R, Rest...> {
+    template<int PP>
+    static __device__ __forceinline__ void run(float2 (&v)[PP], float2 *buf, const float2 *tw, int tid)
+    {
+        using PS = Pass<M, TN, R, NS, false>;
+        group_sync<TN>(); // previous pass's stores are visible
+        PS::load_smem(v, buf, tid);
+        group_sync<TN>(); // everyone has read before anyone overwrites
+        PS::compute_store(v, buf, tw, tid);
+        LaterPasses<M, TN, NS * R, Rest...>::run(v, buf, tw, tid);
+    }
+};
+
+template<int N, typename PlanType>
+struct Fft;
+template<int N, int TN_, int R0, int... Rest>
+struct Fft<N, PlanT<TN_, R0, Rest...>> {
+    static constexpr int M = N / 2;
+    static constexpr int TN = TN_;
+    static constexpr int P = M / TN;
+    using P0 = Pass<M, TN, R0, 1, true>;
+
+    // Loads the frame (as M complex points), applies the window, reports whether any sample is nonzero.
+    static __device__ __forceinline__ bool load_frame(float2 (&v)[P], const float *frame, const KParams &p, int tid)
+    {
+        bool nz = false;
+        if(p.aligned8)
+        {
+            const float2 *f2 = reinterpret_cast<const float2 *>(frame);
+#pragma unroll
+            for(int b = 0; b < P0::BPT; ++b)
+#pragma unroll
+                for(int t = 0; t < R0; ++t)
+                    v[b * R0 + t] = ldg_stream_f2(f2 + (tid + b * TN + t * P0::BF));
+        }
+        else
+        {
+#pragma unroll
+            for(int b = 0; b < P0::BPT; ++b)
+#pragma unroll
+                for(int t = 0; t < R0; ++t)
+                {
+                    const int n = tid + b * TN + t * P0::BF;
+                    v[b * R0 + t] = make_float2(ldg_stream_f1(frame + 2 * n), ldg_stream_f1(frame + 2 * n + 1));
+                }
+        }
+#pragma unroll
+        for(int i = 0; i < P; ++i)
+            nz |= (v[i].x != 0.0f) | (v[i].y != 0.0f);
+        if(p.window2 != nullptr)
+        {
+#pragma unroll
+            for(int b = 0; b < P0::BPT; ++b)
+#pragma unroll
+                for(int t = 0; t < R0; ++t)
+                {
+                    const float2 w = __ldg(p.window2 + (tid + b * TN + t * P0::BF));
+                    v[b * R0 + t].x *= w.x;
+                    v[b * R0 + t].y *= w.y;
+                }
+        }
+        return nz;
+    }
+
+    // Complex FFT of the M points in v; result X[k] (natural order) is left in buf[phys(k)].
+    static __device__ __forceinline__ void run(float2 (&v)[P], float2 *buf, const float2 *tw, int tid)
+    {
+        group_sync<TN>(); // previous consumers of buf are done
+        P0::compute_store(v, buf, tw, tid);
+        LaterPasses<M, TN, R0, Rest...>::run(v, buf, tw, tid);
+        group_sync<TN>(); // X visible to the whole group
+    }
+};
+
+// kernel_convolve, src/filter.hpp:160-169 (sequential mul+add, no contraction)
+__device__ __forceinline__ float kernel_convolve(const float *db, int sz, const float *__restrict__ w, int radius, int index)
+{
+    const int start = (index - radius) + 1;
+    const int stop = min(index + radius + 1, sz);
+    float sum = 0.0f;
+    for(int i = max(start, 0); i < stop; ++i)
+        sum = __fadd_rn(sum, __fmul_rn(db[i], __ldg(w + (i - start))));
+    return sum;
+}
+
+// One display point (curve) or one bar from the dB spectrum of a display channel held in shared memory.
+// src/filter.hpp:182-211, src/source.cpp:1392-1394,1523-1532
+__device__ __forceinline__ float interp_point(const KParams &p, const float *db, int B, int i)
+{
+    if(!p.display_bar)
+    {
+        const float x = __ldg(p.interp_idx + i);
+        if(p.interp_mode == 0)
+            return db[(int)x];
+        return kernel_convolve(db, B, p.interp_w + (size_t)i * p.taps, p.radius, (int)x);
+    }
+    const int count = __ldg(p.band_widths + i);
+    float sum = 0.0f;
+    if(p.interp_mode == 0)
+    {
+        const int base = (int)__ldg(p.interp_idx + i);
+        for(int j = 0; j < count; ++j)
+            sum = __fadd_rn(sum, db[base + j]);
+    }
+    else
+    {
+        const int off = __ldg(p.band_offsets + i);
+        for(int j = 0; j < count; ++j)
+            sum = __fadd_rn(sum, kernel_convolve(db, B, p.interp_w + (size_t)(off + j) * p.taps, p.radius,
+                                                 (int)__ldg(p.interp_idx + off + j)));
+    }
+    return __fdiv_rn(sum, (float)count);
+}
+
+// weighted_avg, src/filter.hpp:133-158
+__device__ __forceinline__ float weighted_avg(const KParams &p, const float *samples, int n, int index)
+{
+    const int start = (index - p.gauss_radius) + 1;
+    const int stop = index + p.gauss_radius;
+    float sum = 0.0f;
+    if((start < 0) || (stop > n))
+    {
+        const int loopstart = max(start, 0);
+        const int loopstop = min(stop, n);
+        float wsum = 0.0f;
+        for(int i = loopstart; i < loopstop; ++i)
+        {
+            const float weight = __ldg(p.gauss_w + (i - start));
+            wsum = __fadd_rn(wsum, weight);
+            sum = __fadd_rn(sum, __fmul_rn(samples[i], weight));
+        }
+        return __fdiv_rn(sum, wsum);
+    }
+    for(int i = start; i < stop; ++i)
+        sum = __fadd_rn(sum, __fmul_rn(samples[i], __ldg(p.gauss_w + (i - start))));
+    return __fdiv_rn(sum, p.gauss_sum);
+}
+
+// ---- the fused kernel ------------------------------------------------------------------------------
+template<int N, int CC>
+__global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_constant__ KParams p)
+{
+    using G = Geo<N>;
+    using F = Fft<N, typename Plan<N>::type>;
+    constexpr int M = G::M, B = G::M, TN = G::TN, P = G::P;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *smem = reinterpret_cast<float2 *>(smem_raw);
+    const int grp = threadIdx.x / TN;
+    const int tid = threadIdx.x % TN;
+    float2 *buf = smem + (size_t)grp * G::BUF;
+    float *dbs = reinterpret_cast<float *>(buf); // dB spectrum [dch][B] overlays the exchange buffer
+    float *pts = reinterpret_cast<float *>(smem + (size_t)G::GROUPS * G::BUF) + (size_t)grp * 2 * p.n_points;
+    __shared__ float red_scratch[32];
+
+    const int s_raw = blockIdx.x * G::GROUPS + grp;
+    const bool active = s_raw < p.n_streams;
+    const int s = active ? s_raw : (p.n_streams - 1);
+
+    const int dch = p.dch, och = p.och;
+    const bool stereo = p.stereo != 0;
+
+    // ---- per-stream state -> registers ----
+    float st[CC][P];
+    {
+        const float *sp = p.state + (size_t)s * CC * B;
+#pragma unroll
+        for(int c = 0; c < CC; ++c)
+#pragma unroll
+            for(int i = 0; i < P; ++i)
+                st[c][i] = sp[c * B + tid + i * TN];
+    }
+    const unsigned char fl = p.flags[s];
+    bool last_silent = (fl & 1u) != 0;
+    bool prev_out_silent0 = (fl & 2u) != 0;
+    bool prev_out_silent1 = (fl & 4u) != 0;
+
+    const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
+    float *hold_s = p.hold_db + (size_t)s * och * B;
+
+    for(int t = 0; t < p.n_frames; ++t)
+    {
+        const bool skip_all = (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * p.n_frames + t] != 0);
+        bool proc[2] = {false, false};
+        unsigned silent_channels = 0;
+
+        // where the previous tick's m_decibels can be re-read (only on rare gate paths)
+        const float *prev_db =
+            (p.out_db != nullptr && t > 0) ? p.out_db + ((size_t)s * p.n_frames + (t - 1)) * dch * B : hold_s;
+        const int prev_slot_stride = B;
+
+#pragma unroll
+        for(int c = 0; c < CC; ++c)
+        {
+            float2 v[P];
+            const float *frame = pcm_s + (size_t)c * p.channel_stride + (size_t)t * p.hop;
+            const bool nz = group_any<TN>(F::load_frame(v, frame, p, tid));
+            F::run(v, buf, p.tw, tid);
+
+            // ---- gate, src/source_generic.cpp:63-95 ----
+            bool do_proc = !skip_all;
+            if(!skip_all)
+            {
+                const bool silent = !nz;
+                if(!silent)
+                    last_silent = false;
+                if(silent && p.gate)
+                {
+                    if(last_silent)
+                        do_proc = false;
+                    else
+                    {
+                        // m_decibels[stereo ? channel : 0] all <= floor-10 ?  In mono-mix the second channel looks at
+                        // slot 0, which holds channel 0's fresh LINEAR magnitudes (>= 0 > floor-10) if that was processed.
+                        bool outsilent;
+                        if(stereo)
+                            outsilent = (c == 0) ? prev_out_silent0 : prev_out_silent1;
+                        else
+                            outsilent = (c == 1 && proc[0]) ? false : prev_out_silent0;
+                        if(outsilent)
+                        {
+                            if(++silent_channels >= (unsigned)CC)
+                                last_silent = true;
+                            do_proc = false;
+                        }
+                    }
+                }
+            }
+            proc[c] = do_proc;
+
+            // ---- split pass + magnitude + slope + EMA, src/source_generic.cpp:110-135 ----
+            // (computed unconditionally; committed to the state registers only if the channel is processed)
+#pragma unroll
+            for(int i = 0; i < P; ++i)
+            {
+                const int k = tid + i * TN;
+                const float2 a = buf[phys(k)];
+                float2 b = buf[phys((M - k) & (M - 1))];
+                b.y = -b.y;
+                const float2 sum = cadd(a, b);
+                const float2 dif = csub(a, b);
+                const float2 o = make_float2(dif.y, -dif.x); // -i (a - b)
+                const float2 w = __ldg(p.tw_post + k);
+                const float2 y = cadd(sum, cmul(o, w));
+                float mag = sqrtf(fmaf(y.x, y.x, y.y * y.y)) * p.coef_half;
+                if(p.slope != nullptr)
+                    mag *= __ldg(p.slope + k);
+                if(p.tsmooth)
+                {
+                    float oldval = st[c][i];
+                    if(p.fast_peaks)
+                        oldval = fmaxf(mag, oldval);
+                    mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+                }
+                if(do_proc)
+                    st[c][i] = mag;
+            }
+        }
+
+        // ---- outputs ----
+        float vc = 0.0f;
+        if(p.normalize)
+        {
+            const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * p.n_frames + t] : 0.0f;
+            vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain); // src/source_generic.cpp:163
+        }
+        float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * p.n_frames + t) * dch * B : nullptr;
+        const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
+        const bool want_points = p.out_points != nullptr;
+        if(want_points)
+            group_sync<TN>(); // split-pass reads of buf are done before dB overwrites it
+
+        float peak = -INFINITY;
+        bool outs0 = true, outs1 = true;
+        for(int d = 0; d < dch; ++d)
+        {
+            bool outs = true;
+#pragma unroll
+            for(int i = 0; i < P; ++i)
+            {
+                const int k = tid + i * TN;
+                float outv;
+                if(last_silent)
+                {
+                    // tick returned early (src/source_generic.cpp:138-139): m_decibels unchanged
+                    outv = prev_db[d * prev_slot_stride + k];
+                }
+                else
+                {
+                    float in;
+                    if(CC == 2 && !stereo)
+                    {
+                        // 2 channels mixed to mono: dbfs((m0 + m1) * 0.5), src/source_generic.cpp:150-154
+                        const float in0 = proc[0] ? st[0][i] : prev_db[k];
+                        const float in1 = st[CC - 1][i];
+                        in = (in0 + in1) * 0.5f;
+                    }
+                    else
+                    {
+                        // stereo with 2 channels: slot d <- channel d; mono source shown as stereo: slot 1 = copy of slot 0
+                        const int c = (CC == 2) ? d : 0;
+                        in = proc[c] ? st[c][i] : prev_db[c * prev_slot_stride + k];
+                    }
+                    outv = dbfs(in, p.db_min);
+                    if(k >= 1)
+                    {
+                        if(p.normalize)
+                            outv += vc; // src/source_generic.cpp:161-167
+                        if(p.rolloff != nullptr)
+                            outv = fmaxf(outv - __ldg(p.rolloff + k), p.db_min); // :169-179
+                    }
+                }
+                outs &= !(outv > p.floor_m10);
+                if(k >= 1)
+                    peak = fmaxf(peak, outv);
+                if(active)
+                {
+                    if(odb != nullptr)
+                        stg_stream(odb + d * B + k, outv);
+                    if(mirror_each_frame)
+                        hold_s[d * B + k] = outv;
+                }
+                if(want_points)
+                    dbs[d * B + k] = outv;
+            }
+            if(d == 0)
+                outs0 = outs;
+            else
+                outs1 = outs;
+        }
+        if(!last_silent && p.gate)
+        {
+            prev_out_silent0 = group_all<TN>(outs0);
+            if(dch > 1)
+                prev_out_silent1 = group_all<TN>(outs1);
+        }
+        if(p.out_silent != nullptr && active && tid == 0)
+            p.out_silent[(size_t)s * p.n_frames + t] = last_silent ? 1 : 0;
+        if(p.out_peak != nullptr)
+        {
+            const float gm = group_max<TN>(peak, red_scratch);
+            if(active && tid == 0)
+                atomic_max_float(p.out_peak + t, gm);
+        }
+
+        // ---- display points: interpolation (+ gaussian) from the dB spectrum in shared memory ----
+        if(want_points)
+        {
+            group_sync<TN>();
+            float *opt = p.out_points + ((size_t)s * p.n_frames + t) * dch * p.n_points;
+            for(int d = 0; d < dch; ++d)
+            {
+                const float *db = dbs + d * B;
+                if(!p.filter)
+                {
+                    for(int i = tid; i < p.n_points; i += TN)
+                    {
+                        const float val = interp_point(p, db, B, i);
+                        if(active)
+                            stg_stream(opt + d * p.n_points + i, val);
+                    }
+                }
+                else
+                {
+                    float *pp = pts + d * p.n_points;
+                    for(int i = tid; i < p.n_points; i += TN)
+                        pp[i] = interp_point(p, db, B, i);
+                    group_sync<TN>();
+                    for(int i = tid; i < p.n_points; i += TN)
+                    {
+                        const float val = weighted_avg(p, pp, p.n_points, i);
+                        if(active)
+                            stg_stream(opt + d * p.n_points + i, val);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- state back to the engine ----
+    if(active)
+    {
+        float *sp = p.state + (size_t)s * CC * B;
+#pragma unroll
+        for(int c = 0; c < CC; ++c)
+#pragma unroll
+            for(int i = 0; i < P; ++i)
+                sp[c * B + tid + i * TN] = st[c][i];
+        if(p.write_hold && p.out_db != nullptr && p.n_frames > 0)
+        {
+            // m_decibels mirror := outputs of the last tick (slot 1 of a mono mix keeps linear channel-1 magnitudes)
+            const float *last = p.out_db + ((size_t)s * p.n_frames + (p.n_frames - 1)) * dch * B;
+            for(int d = 0; d < dch; ++d)
+#pragma unroll
+                for(int i = 0; i < P; ++i)
+                    hold_s[d * B + tid + i * TN] = last[d * B + tid + i * TN];
+        }
+        if(CC == 2 && !stereo && p.write_hold)
+        {
+#pragma unroll
+            for(int i = 0; i < P; ++i)
+                hold_s[B + tid + i * TN] = st[1][i];
+        }
+        if(tid == 0)
+            p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent0 ? 2u : 0u) | (prev_out_silent1 ? 4u : 0u));
+    }
+}
+
+// peak normalisation pass: out[row][k] += gain[t] for k >= 1 (row = (stream, frame, channel))
+__global__ void peak_normalize_kernel(float *data, int n_streams, int n_frames, int rows_per_frame, int row_len,
+                                      const float *peak, float target_db, float max_gain)
+{
+    const long long rows = (long long)n_streams * n_frames * rows_per_frame;
+    for(long long r = blockIdx.x; r < rows; r += gridDim.x)
+    {
+        const int t = (int)((r / rows_per_frame) % n_frames);
+        const float gain = fminf(target_db - peak[t], max_gain);
+        float *row = data + r * row_len;
+        for(int k = 1 + threadIdx.x; k < row_len; k += blockDim.x)
+            row[k] += gain;
+    }
+}
+
+__global__ void fill_kernel(float *p, long long n, float v)
+{
+    for(long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+} // namespace wf

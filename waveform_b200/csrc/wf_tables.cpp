@@ -1,0 +1,369 @@
+// wf_tables.cpp — see wf_tables.hpp.  Host-only, setup-time.
+#include "wf_tables.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <limits>
+#include <numbers>
+
+namespace wf {
+
+namespace {
+
+constexpr float kPi = std::numbers::pi_v<float>;
+
+// log_interp, src/math_funcs.hpp:25-29
+inline float log_interp(float a, float b, float t) { return a * std::pow(b / a, t); }
+
+// sinc / lanczos, src/math_funcs.hpp:37-52
+inline float sinc(float x)
+{
+    if(x == 0.0)
+        return 1.0f;
+    const auto tmp = kPi * x;
+    return std::sin(tmp) / tmp;
+}
+inline float lanczos(float x, float w) { return (std::abs(x) < w) ? sinc(x) * sinc(x / w) : 0.0f; }
+
+// window coefficients + sequential fp32 sum, src/source.cpp:1190-1234
+void build_window(Tables &t)
+{
+    const auto &c = t.cfg;
+    const size_t n = (size_t)t.N;
+    if(c.window == WF_WINDOW_NONE)
+    {
+        t.window.clear();
+        t.window_sum = (float)n;
+        return;
+    }
+    t.window.resize(n);
+    const auto N = n - 1;
+    constexpr auto pi2 = 2 * kPi;
+    constexpr auto pi4 = 4 * kPi;
+    constexpr auto pi6 = 6 * kPi;
+    auto *w = t.window.data();
+    switch(c.window)
+    {
+    case WF_WINDOW_HAMMING:
+        for(size_t i = 0; i < n; ++i)
+            w[i] = 0.53836f - (0.46164f * std::cos((pi2 * i) / N));
+        break;
+    case WF_WINDOW_BLACKMAN:
+        for(size_t i = 0; i < n; ++i)
+            w[i] = 0.42f - (0.5f * std::cos((pi2 * i) / N)) + (0.08f * std::cos((pi4 * i) / N));
+        break;
+    case WF_WINDOW_BLACKMAN_HARRIS:
+        for(size_t i = 0; i < n; ++i)
+            w[i] = 0.35875f - (0.48829f * std::cos((pi2 * i) / N)) + (0.14128f * std::cos((pi4 * i) / N)) -
+                   (0.01168f * std::cos((pi6 * i) / N));
+        break;
+    case WF_WINDOW_POWER_OF_SINE:
+        for(size_t i = 0; i < n; ++i)
+            w[i] = std::pow(std::sin((kPi * i) / N), (float)c.sine_exponent);
+        break;
+    case WF_WINDOW_HANN:
+    default:
+        for(size_t i = 0; i < n; ++i)
+            w[i] = 0.5f * (1 - std::cos((pi2 * i) / N));
+        break;
+    }
+    auto sum = 0.0f;
+    for(size_t i = 0; i < n; ++i)
+        sum += w[i];
+    t.window_sum = sum;
+}
+
+// slope modifiers, src/source.cpp:1282-1290
+void build_slope(Tables &t)
+{
+    t.slope.clear();
+    if(!(t.cfg.slope > 0.0f))
+        return;
+    const auto num_mods = (size_t)t.B;
+    const auto maxmod = (float)(num_mods - 1);
+    t.slope.resize(num_mods);
+    for(size_t i = 0; i < num_mods; ++i)
+        t.slope[i] = std::log10(log_interp(10.0f, 10000.0f, ((float)i * t.cfg.slope) / maxmod));
+}
+
+// roll-off, init_rolloff src/source.cpp:898-918
+void build_rolloff(Tables &t)
+{
+    t.rolloff.clear();
+    const auto &c = t.cfg;
+    if(!((c.rolloff_q > 0.0f) && (c.rolloff_rate > 0.0f)))
+        return;
+    const auto sz = (size_t)t.B;
+    const auto sr = (float)c.sample_rate;
+    const auto coeff = sr / (float)(size_t)t.N;
+    const auto ratio = std::exp2(c.rolloff_q);
+    const auto freq_low = (float)c.cutoff_low * ratio;
+    const auto freq_high = (float)c.cutoff_high / ratio;
+    t.rolloff.resize(sz);
+    t.rolloff[0] = 0.0f;
+    for(size_t i = 1u; i < sz; ++i)
+    {
+        auto freq = i * coeff;
+        auto ratio_low = freq_low / freq;
+        auto ratio_high = freq / freq_high;
+        auto low_attenuation = (ratio_low > 1.0f) ? (c.rolloff_rate * std::log2(ratio_low)) : 0.0f;
+        auto high_attenuation = (ratio_high > 1.0f) ? (c.rolloff_rate * std::log2(ratio_high)) : 0.0f;
+        t.rolloff[i] = low_attenuation + high_attenuation;
+    }
+}
+
+// make_catrom_kernel, src/filter.hpp:67-103
+void build_catrom(Tables &t, float tension)
+{
+    const float m[4][4] = {{0, -tension, 2 * tension, -tension},
+                           {1, 0, tension - 3, 2 - tension},
+                           {0, tension, 3 - (2 * tension), tension - 2},
+                           {0, 0, -tension, tension}};
+    const auto size = (intmax_t)t.interp_indices.size();
+    t.interp_radius = 2;
+    t.interp_taps = 4;
+    t.interp_weights.assign((size_t)size * 4, 0.0f);
+    for(intmax_t i = 0; i < size; ++i)
+    {
+        auto u = t.interp_indices[i] - std::floor(t.interp_indices[i]);
+        float row[4] = {1, u, u * u, u * u * u};
+        for(intmax_t j = 0; j < 4; ++j)
+        {
+            float sum = 0;
+            for(intmax_t k = 0; k < 4; ++k)
+                sum += row[k] * m[j][k];
+            t.interp_weights[(i * 4) + j] = sum;
+        }
+    }
+}
+
+// make_lanczos_kernel, src/filter.hpp:106-131
+void build_lanczos(Tables &t, intmax_t radius)
+{
+    const auto size = (intmax_t)t.interp_indices.size();
+    t.interp_radius = (int)radius;
+    t.interp_taps = (int)(radius * 2);
+    t.interp_weights.assign((size_t)(size * radius * 2), 0.0f);
+    const auto fradius = (float)radius;
+    for(intmax_t i = 0; i < size; ++i)
+    {
+        const auto x = t.interp_indices[i];
+        const auto ix = (intmax_t)x;
+        const auto start = ix - radius + 1;
+        const auto stop = ix + radius;
+        const auto base = i * radius * 2;
+        for(auto j = start; j <= stop; ++j)
+            t.interp_weights[base + (j - start)] = lanczos(x - j, fradius);
+    }
+}
+
+// init_interp, src/source.cpp:837-896 (spectrum display modes only)
+void build_interp(Tables &t, unsigned sz)
+{
+    const auto &c = t.cfg;
+    const size_t fft_size = (size_t)t.N;
+    const auto maxbin = (fft_size / 2) - 1;
+    const auto sr = (float)c.sample_rate;
+    const float lowbin = std::clamp((float)c.cutoff_low * fft_size / sr, 1.0f, (float)maxbin);
+    const float highbin = std::clamp((float)c.cutoff_high * fft_size / sr, 1.0f, (float)maxbin);
+
+    t.interp_indices.resize(sz);
+    for(auto i = 0u; i < sz; ++i)
+    {
+        const float pos = (c.mirror_freq_axis ? i * 2.0f : (float)i) / (float)(sz - 1);
+        const float v = c.log_scale ? log_interp(lowbin, highbin, pos) : std_lerp(lowbin, highbin, pos);
+        t.interp_indices[i] = std::clamp(v, lowbin, highbin);
+    }
+
+    const bool bars = (c.display_mode == WF_DISPLAY_BAR);
+    t.band_widths.clear();
+    t.band_offsets.clear();
+    if(bars)
+    {
+        t.band_widths.resize((size_t)t.num_bars);
+        for(auto i = 0; i < t.num_bars; ++i)
+            t.band_widths[i] = std::max((int)(t.interp_indices[i + 1] - t.interp_indices[i]), 1);
+        t.band_offsets.resize((size_t)t.num_bars + 1);
+        int32_t acc = 0;
+        for(auto i = 0; i < t.num_bars; ++i)
+        {
+            t.band_offsets[i] = acc;
+            acc += t.band_widths[i];
+        }
+        t.band_offsets[t.num_bars] = acc;
+    }
+
+    t.interp_weights.clear();
+    t.interp_radius = 0;
+    t.interp_taps = 0;
+    if(c.interp_mode != WF_INTERP_POINT)
+    {
+        if(bars)
+        {
+            // m_interp_indices so far holds band starts; fill in every sample point of every band (:876-889)
+            std::vector<float> samples;
+            for(auto i = 0; i < t.num_bars; ++i)
+            {
+                auto count = t.band_widths[i];
+                for(auto j = 0; j < count; ++j)
+                    samples.push_back(t.interp_indices[i] + j);
+            }
+            t.interp_indices = std::move(samples);
+        }
+        if(c.interp_mode == WF_INTERP_LANCZOS)
+            build_lanczos(t, 4);
+        else
+            build_catrom(t, 0.5f);
+    }
+}
+
+// make_gauss_kernel, src/filter.hpp:40-65
+void build_gauss(Tables &t)
+{
+    t.gauss.clear();
+    t.gauss_radius = 0;
+    t.gauss_sum = 0.0f;
+    if(t.cfg.filter_mode != WF_FILTER_GAUSS)
+        return;
+    float sigma = std::max(std::abs(t.cfg.filter_radius), 0.01f);
+    auto w = (int)std::ceil(3.0f * sigma);
+    auto size = (2 * w) - 1;
+    t.gauss.resize((size_t)size);
+    t.gauss_radius = w;
+    constexpr auto pi2 = kPi * 2.0f;
+    const auto sigsqr = sigma * sigma;
+    const auto expdenom = 2.0f * sigsqr;
+    const auto coeff = (1.0f / (std::sqrt(pi2) * sigma));
+    auto j = 0;
+    for(auto i = -w + 1; i < w; ++i)
+    {
+        auto exponent = -((i * i) / expdenom);
+        auto weight = coeff * std::exp(exponent);
+        t.gauss[j++] = weight;
+        t.gauss_sum += weight;
+    }
+}
+
+void build_twiddles(Tables &t)
+{
+    const int M = t.N / 2;
+    t.tw.resize((size_t)M * 2);
+    t.tw_post.resize((size_t)M * 2);
+    for(int k = 0; k < M; ++k)
+    {
+        const double a = -2.0 * std::numbers::pi * (double)k / (double)M;
+        t.tw[2 * k] = (float)std::cos(a);
+        t.tw[2 * k + 1] = (float)std::sin(a);
+        const double b = -2.0 * std::numbers::pi * (double)k / (double)t.N;
+        t.tw_post[2 * k] = (float)std::cos(b);
+        t.tw_post[2 * k + 1] = (float)std::sin(b);
+    }
+}
+
+} // namespace
+
+// std::lerp(float, float, float) as evaluated by libstdc++ (P0811R3 algorithm); the reference's lerp()
+// (src/math_funcs.hpp:31-35) forwards to it.
+float std_lerp(float a, float b, float t)
+{
+    if((a <= 0 && b >= 0) || (a >= 0 && b <= 0))
+        return t * b + (1 - t) * a;
+    if(t == 1)
+        return b;
+    const float x = a + t * (b - a);
+    return ((t > 1) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+}
+
+// WAVSource::get_gravity, src/source.hpp:301-312
+float gravity_for(const wf_config &c, float seconds)
+{
+    constexpr float denom = 0.03868924705242879469662125316986f;
+    constexpr float hi = denom * 5.0f;
+    constexpr float lo = 0.0f;
+    if((c.tsmoothing == WF_TSMOOTH_NONE) || (c.gravity <= 0.0f))
+        return 0.0f;
+    return (c.tsmoothing == WF_TSMOOTH_TVEXPONENTIAL) ? std::exp(-seconds / std_lerp(lo, hi, c.gravity)) : c.gravity;
+}
+
+int build_tables(const wf_config &cfg_in, Tables &t, const char **why)
+{
+    t = Tables{};
+    t.cfg = cfg_in;
+    auto &c = t.cfg;
+    auto fail = [&](const char *msg) {
+        if(why)
+            *why = msg;
+        return (int)WF_ERR_INVALID_ARG;
+    };
+
+    // get_settings clamps, src/source.cpp:562-577
+    if(c.fft_size < 128)
+        c.fft_size = 128;
+    else if(c.fft_size & 15)
+        c.fft_size &= -16;
+    if((c.cutoff_high - c.cutoff_low) < 0)
+    {
+        c.cutoff_high = 17500;
+        c.cutoff_low = 120;
+    }
+    if((c.ceiling_db - c.floor_db) < 1)
+    {
+        c.ceiling_db = 0;
+        c.floor_db = -120;
+    }
+    if(c.capture_channels < 1 || c.capture_channels > 2)
+        return fail("capture_channels must be 1 or 2 (the plugin captures at most 2, src/source.cpp:1089)");
+    if(c.sample_rate == 0)
+        return fail("sample_rate must be > 0");
+    if(c.max_streams < 1)
+        return fail("max_streams must be >= 1");
+    if(c.window < WF_WINDOW_NONE || c.window > WF_WINDOW_POWER_OF_SINE)
+        return fail("unknown window");
+    if(c.tsmoothing < WF_TSMOOTH_NONE || c.tsmoothing > WF_TSMOOTH_TVEXPONENTIAL)
+        return fail("unknown tsmoothing mode");
+    if(c.interp_mode < WF_INTERP_POINT || c.interp_mode > WF_INTERP_CATROM)
+        return fail("unknown interp_mode");
+    if(c.display_mode < WF_DISPLAY_CURVE || c.display_mode > WF_DISPLAY_BAR)
+        return fail("unknown display_mode");
+    if(c.width < 2 || c.width > 16384)
+        return fail("width out of range");
+    if(c.display_mode == WF_DISPLAY_BAR && (c.bar_width < 1 || c.bar_gap < 0))
+        return fail("bar_width must be >= 1 and bar_gap >= 0");
+    c.stereo = c.stereo ? 1 : 0;
+
+    t.N = c.fft_size;
+    t.B = t.N / 2;
+    t.output_channels = ((c.capture_channels > 1) || c.stereo) ? 2 : 1; // src/source.cpp:1170
+    t.display_channels = c.stereo ? 2 : 1;
+    t.db_min = 20.0f * std::log10(std::numeric_limits<float>::min()); // src/source.cpp:43
+
+    build_window(t);
+
+    // display points, src/source.cpp:1250-1276
+    if(c.display_mode == WF_DISPLAY_CURVE)
+    {
+        t.num_bars = 0;
+        t.num_points = c.width;
+        build_interp(t, (unsigned)c.width);
+    }
+    else
+    {
+        const auto bar_stride = c.bar_width + c.bar_gap;
+        t.num_bars = (int)((unsigned)c.width / (unsigned)bar_stride);
+        if(((int)c.width - (t.num_bars * bar_stride)) >= c.bar_width)
+            ++t.num_bars;
+        if(t.num_bars < 1)
+            return fail("width too small for one bar");
+        t.num_points = t.num_bars;
+        build_interp(t, (unsigned)(t.num_bars + 1)); // extra band for the last bar
+    }
+
+    build_gauss(t);
+    build_slope(t);
+    build_rolloff(t);
+    build_twiddles(t);
+    return WF_OK;
+}
+
+} // namespace wf
