@@ -8,13 +8,16 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
 #include <vector>
 
 #include "wf_kernels.cuh"
+#include "wf_fast2048.cuh"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -29,6 +32,7 @@ struct wf_engine {
     bool ev_valid = false;
     std::string last_error;
     int64_t launches = 0;
+    bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
 
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
@@ -154,6 +158,52 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     case 32768: return launch_fused<32768, CC>(e, kp, st, extra);
     default: return set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d has no kernel", e->tab.N);
     }
+}
+
+template<bool WIN, bool TSM, bool GATE, bool EXTRA>
+int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
+{
+    static thread_local bool configured[8] = {false};
+    const int dev = e->device & 7;
+    if(!configured[dev])
+    {
+        WF_CUDA(e, cudaFuncSetAttribute(stft2048_fast_kernel<WIN, TSM, GATE, EXTRA>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, fast::kSmemBytes));
+        configured[dev] = true;
+    }
+    const int ctas_needed = (kp.n_streams + fast::kWarpsPerCta - 1) / fast::kWarpsPerCta;
+    const int grid = std::min(ctas_needed, e->sm_count * 2);
+    stft2048_fast_kernel<WIN, TSM, GATE, EXTRA><<<grid, fast::kThreads, fast::kSmemBytes, st>>>(kp);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return WF_OK;
+}
+
+// Hand-specialised path for the headline shape (see wf_fast2048.cuh); everything else takes the generic kernel.
+int dispatch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
+{
+    const bool win = kp.window2 != nullptr, tsm = kp.tsmooth != 0, gate = kp.gate != 0;
+#define WF_FAST_CASE(W, T, G, X)            \
+    if(win == W && tsm == T && gate == G && extra == X) \
+        return launch_fast2048<W, T, G, X>(e, kp, st);
+    WF_FAST_CASE(true, true, true, false)
+    WF_FAST_CASE(true, true, true, true)
+    WF_FAST_CASE(true, true, false, false)
+    WF_FAST_CASE(true, true, false, true)
+    WF_FAST_CASE(true, false, true, false)
+    WF_FAST_CASE(true, false, true, true)
+    WF_FAST_CASE(true, false, false, false)
+    WF_FAST_CASE(true, false, false, true)
+    WF_FAST_CASE(false, true, true, false)
+    WF_FAST_CASE(false, true, true, true)
+    WF_FAST_CASE(false, true, false, false)
+    WF_FAST_CASE(false, true, false, true)
+    WF_FAST_CASE(false, false, true, false)
+    WF_FAST_CASE(false, false, true, true)
+    WF_FAST_CASE(false, false, false, false)
+    WF_FAST_CASE(false, false, false, true)
+#undef WF_FAST_CASE
+    return set_err(e, WF_ERR_INVALID_ARG, "fast2048 dispatch fell through");
 }
 
 int fill_device(wf_engine *e, float *p, long long n, float v, cudaStream_t st)
@@ -299,6 +349,10 @@ int wf_create(const wf_config *cfg, wf_engine **out)
     if(dev >= ndev)
         return bail(set_err(e, WF_ERR_INVALID_ARG, "device %d out of range (%d devices)", dev, ndev));
     e->device = dev;
+    {
+        const char *fg = getenv("WF_FORCE_GENERIC");
+        e->force_generic = fg && fg[0] == '1';
+    }
 
 #define WF_TRY(x)                 \
     do                            \
@@ -583,7 +637,17 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         }
         extra = (size_t)groups * 2 * (size_t)t.num_points * sizeof(float);
     }
-    int rc = (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
+    const bool aligned16 = (((uintptr_t)pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
+    const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && out_db && !out_points && aligned16 &&
+                         !e->force_generic;
+    int rc;
+    if(fast_ok)
+    {
+        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+        rc = dispatch_fast2048(e, kp, st, x);
+    }
+    else
+        rc = (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
     if(rc)
         return rc;
     WF_CUDA(e, cudaEventRecord(e->ev1, st));

@@ -278,6 +278,8 @@ class Engine:
         if sync and stream is None:
             self._check(self.L.wf_process(self.h, C.byref(b)))
         else:
+            if stream == 0:
+                stream = 1  # the legacy default stream is cudaStreamLegacy (0x1); NULL selects the engine's own stream
             self._check(self.L.wf_process_async(self.h, C.byref(b), stream))
 
     def process(self, pcm, n_frames: int, hop: int, *, first_stream=0, seconds=1.0 / 60.0, input_rms=None,
