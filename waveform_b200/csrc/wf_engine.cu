@@ -33,6 +33,8 @@ struct wf_engine {
     std::string last_error;
     int64_t launches = 0;
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
+    int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
+    int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
 
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
@@ -160,20 +162,45 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     }
 }
 
-template<bool WIN, bool TSM, bool GATE, bool EXTRA>
+// Pick warps/SM so that whole streams (the unit of work: EMA state stays on-chip across a stream's frames)
+// spread evenly over the SMs:  rounds * warps_per_sm * sm_count >= n_streams with the least waste.
+static void fast2048_geometry(int n_streams, int sm_count, int max_wpc, int *warps_per_cta, int *grid)
+{
+    int best_w = max_wpc, best_cost = 1 << 30;
+    for(int w = max_wpc; w >= 8; --w) // one CTA per SM with w warps
+    {
+        const int rounds = (n_streams + sm_count * w - 1) / (sm_count * w);
+        const int cost = rounds * w; // time ~ rounds * (per-SM issue load ~ w warps sharing the SM)
+        if(cost < best_cost)
+        {
+            best_cost = cost;
+            best_w = w;
+        }
+    }
+    *warps_per_cta = best_w;
+    const int ctas_needed = (n_streams + best_w - 1) / best_w;
+    *grid = std::min(ctas_needed, sm_count);
+}
+
+template<int MAXW, bool TSM, bool GATE, bool EXTRA>
 int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
 {
     static thread_local bool configured[8] = {false};
     const int dev = e->device & 7;
     if(!configured[dev])
     {
-        WF_CUDA(e, cudaFuncSetAttribute(stft2048_fast_kernel<WIN, TSM, GATE, EXTRA>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, fast::kSmemBytes));
+        WF_CUDA(e, cudaFuncSetAttribute(stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, fast::smem_bytes(MAXW)));
         configured[dev] = true;
     }
-    const int ctas_needed = (kp.n_streams + fast::kWarpsPerCta - 1) / fast::kWarpsPerCta;
-    const int grid = std::min(ctas_needed, e->sm_count * 2);
-    stft2048_fast_kernel<WIN, TSM, GATE, EXTRA><<<grid, fast::kThreads, fast::kSmemBytes, st>>>(kp);
+    int wpc = MAXW, grid = 1;
+    fast2048_geometry(kp.n_streams, e->sm_count, MAXW, &wpc, &grid);
+    if(e->fast_wpc_override > 0 && e->fast_wpc_override <= MAXW)
+    {
+        wpc = e->fast_wpc_override;
+        grid = std::min((kp.n_streams + wpc - 1) / wpc, e->sm_count);
+    }
+    stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA><<<grid, wpc * 32, fast::smem_bytes(wpc), st>>>(kp);
     WF_CUDA(e, cudaGetLastError());
     e->launches++;
     return WF_OK;
@@ -182,26 +209,27 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
 // Hand-specialised path for the headline shape (see wf_fast2048.cuh); everything else takes the generic kernel.
 int dispatch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
 {
-    const bool win = kp.window2 != nullptr, tsm = kp.tsmooth != 0, gate = kp.gate != 0;
+    const bool tsm = kp.tsmooth != 0, gate = kp.gate != 0;
+    const int maxw = e->fast_maxw;
 #define WF_FAST_CASE(W, T, G, X)            \
-    if(win == W && tsm == T && gate == G && extra == X) \
+    if(maxw == W && tsm == T && gate == G && extra == X) \
         return launch_fast2048<W, T, G, X>(e, kp, st);
-    WF_FAST_CASE(true, true, true, false)
-    WF_FAST_CASE(true, true, true, true)
-    WF_FAST_CASE(true, true, false, false)
-    WF_FAST_CASE(true, true, false, true)
-    WF_FAST_CASE(true, false, true, false)
-    WF_FAST_CASE(true, false, true, true)
-    WF_FAST_CASE(true, false, false, false)
-    WF_FAST_CASE(true, false, false, true)
-    WF_FAST_CASE(false, true, true, false)
-    WF_FAST_CASE(false, true, true, true)
-    WF_FAST_CASE(false, true, false, false)
-    WF_FAST_CASE(false, true, false, true)
-    WF_FAST_CASE(false, false, true, false)
-    WF_FAST_CASE(false, false, true, true)
-    WF_FAST_CASE(false, false, false, false)
-    WF_FAST_CASE(false, false, false, true)
+    WF_FAST_CASE(16, true, true, false)
+    WF_FAST_CASE(16, true, true, true)
+    WF_FAST_CASE(16, true, false, false)
+    WF_FAST_CASE(16, true, false, true)
+    WF_FAST_CASE(16, false, true, false)
+    WF_FAST_CASE(16, false, true, true)
+    WF_FAST_CASE(16, false, false, false)
+    WF_FAST_CASE(16, false, false, true)
+    WF_FAST_CASE(12, true, true, false)
+    WF_FAST_CASE(12, true, true, true)
+    WF_FAST_CASE(12, true, false, false)
+    WF_FAST_CASE(12, true, false, true)
+    WF_FAST_CASE(12, false, true, false)
+    WF_FAST_CASE(12, false, true, true)
+    WF_FAST_CASE(12, false, false, false)
+    WF_FAST_CASE(12, false, false, true)
 #undef WF_FAST_CASE
     return set_err(e, WF_ERR_INVALID_ARG, "fast2048 dispatch fell through");
 }
@@ -352,6 +380,12 @@ int wf_create(const wf_config *cfg, wf_engine **out)
     {
         const char *fg = getenv("WF_FORCE_GENERIC");
         e->force_generic = fg && fg[0] == '1';
+        const char *mw = getenv("WF_FAST_MAXW");
+        if(mw && (atoi(mw) == 12 || atoi(mw) == 16))
+            e->fast_maxw = atoi(mw);
+        const char *wo = getenv("WF_FAST_WPC");
+        if(wo)
+            e->fast_wpc_override = atoi(wo);
     }
 
 #define WF_TRY(x)                 \

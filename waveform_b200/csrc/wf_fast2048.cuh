@@ -24,11 +24,11 @@ namespace fast {
 constexpr int kN = 2048;
 constexpr int kM = 1024;
 constexpr int kWarpBufBytes = 32 * 33 * 8; // padded transpose buffer, also the TMA landing zone (8192 B used)
-constexpr int kWarpBytes = kWarpBufBytes + 16; // + mbarrier
+constexpr int kStateBytes = 16 * 32 * 8; // EMA state of the stream: [pair q][lane] -> (bin k1, bin k2)
+constexpr int kWarpBytes = kWarpBufBytes + kStateBytes + 16; // + mbarrier
 constexpr int kTableBytes = (1024 + 1024 + 512) * 8;
-constexpr int kWarpsPerCta = 8;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kSmemBytes = kTableBytes + kWarpsPerCta * kWarpBytes;
+constexpr int kMaxWarpsPerCta = 16; // 1 CTA/SM: 16 warps x 12.3 KB + 20 KB tables = 216 KB of shared memory
+constexpr int smem_bytes(int warps_per_cta) { return kTableBytes + warps_per_cta * kWarpBytes; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -73,17 +73,30 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return r;
 }
 
-// dbfs with the MUFU.LG2 path: 20 log10(m) = (20 log10 2) log2(m); __log2f keeps subnormal inputs exact-ish
+__device__ __forceinline__ float lg2_approx_ftz(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// dbfs (src/source.hpp:293-299) on the MUFU.LG2 path: 20 log10(m) = (20 log10 2) log2(m).
+// Normal magnitudes take 3 instructions; zero / subnormal magnitudes (digital silence, the far tail of an EMA
+// decay) take the rare branch, which rescales so that subnormals are still converted exactly like log10f would.
 __device__ __forceinline__ float dbfs_fast(float mag, float db_min)
 {
-    const float l = __log2f(mag) * 6.02059991327962390f;
-    return (mag > 0.0f) ? l : db_min;
+    constexpr float k = 6.02059991327962390f; // 20 log10(2)
+    float o = lg2_approx_ftz(mag) * k;
+    if(mag < 1.17549435e-38f)
+        o = (mag > 0.0f) ? (lg2_approx_ftz(mag * 16777216.0f) - 24.0f) * k : db_min;
+    return o;
 }
 
 } // namespace fast
 
-template<bool WIN, bool TSM, bool GATE, bool EXTRA>
-__global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const __grid_constant__ KParams p)
+// One CTA per SM with up to MAXW warps (16 -> 128 registers/thread, 12 -> 168).  WIN is not a template
+// parameter: without a window the shared "window" table simply holds the magnitude normalisation constant.
+template<int MAXW, bool TSM, bool GATE, bool EXTRA>
+__global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __grid_constant__ KParams p)
 {
     using namespace fast;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -92,15 +105,20 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
     float2 *s_twP = s_twA + 1024; // [q][lane] = W_2048^(lane + 32 q), q < 16
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int warps_per_cta = blockDim.x >> 5;
     unsigned char *wbase = reinterpret_cast<unsigned char *>(s_twP + 512) + warp * kWarpBytes;
     float2 *buf = reinterpret_cast<float2 *>(wbase);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase + kWarpBufBytes);
+    float2 *sst = reinterpret_cast<float2 *>(wbase + kWarpBufBytes) + lane; // this lane's column of the state
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase + kWarpBufBytes + kStateBytes);
 
     // ---- CTA prologue: tables -> shared, mbarriers ----
-    for(int i = threadIdx.x; i < 1024; i += kThreads)
+    // The window table carries the magnitude normalisation (2/sum(w))/2 so the epilogue needs no extra multiply.
+    for(int i = threadIdx.x; i < 1024; i += blockDim.x)
     {
-        if(WIN)
-            s_win[i] = __ldg(p.window2 + i);
+        {
+            const float2 w = (p.window2 != nullptr) ? __ldg(p.window2 + i) : make_float2(1.0f, 1.0f);
+            s_win[i] = make_float2(w.x * p.coef_half, w.y * p.coef_half);
+        }
         s_twA[i] = __ldg(p.tw + (((i >> 5) * (i & 31)) & 1023));
         if(i < 512)
             s_twP[i] = __ldg(p.tw_post + i);
@@ -112,8 +130,8 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
     }
     __syncthreads();
 
-    const int total_warps = gridDim.x * kWarpsPerCta;
-    const int gw = blockIdx.x * kWarpsPerCta + warp;
+    const int total_warps = gridDim.x * warps_per_cta;
+    const int gw = blockIdx.x * warps_per_cta + warp;
     const int S = p.n_streams, T = p.n_frames;
     constexpr int B = kM;
     uint32_t phase = 0;
@@ -122,7 +140,6 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
     const int jp = (32 - lane) & 31;
     const int kb = jp + (lane == 0 ? 32 : 0);
     const int k2_q0 = (lane == 0) ? 512 : (kb + 992);
-    const int pbase = kb; // partner column (+32 selects the extra row for lane 0)
 
     if(gw < S && lane == 0)
     {
@@ -132,23 +149,21 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
 
     for(int s = gw; s < S; s += total_warps)
     {
-        // ---- per-stream state ----
-        float st1[16], st2[16];
+        // ---- per-stream state: global (natural bin order) -> shared ([pair][lane]) ----
         {
             const float *sp = p.state + (size_t)s * B;
 #pragma unroll
             for(int q = 0; q < 16; ++q)
-            {
-                st1[q] = sp[lane + 32 * q];
-                st2[q] = sp[(q == 0) ? k2_q0 : (kb + 32 * (31 - q))];
-            }
+                sst[q * 32] = make_float2(sp[lane + 32 * q], sp[(q == 0) ? k2_q0 : (kb + 32 * (31 - q))]);
         }
         const unsigned char fl = p.flags[s];
         bool last_silent = (fl & 1u) != 0;
         bool prev_out_silent = (fl & 2u) != 0;
+        bool last_from_state = false; // the last tick's outputs are dbfs(state) (normal tick), not a hold / quirk
         const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
         float *hold_s = p.hold_db + (size_t)s * B;
 
+#pragma unroll 1
         for(int t = 0; t < T; ++t)
         {
             // ---- frame from shared (TMA-staged), window in the load prologue ----
@@ -162,87 +177,58 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
                 v[pidx] = buf[lane + 32 * pidx];
                 nzbits |= __float_as_uint(v[pidx].x) | __float_as_uint(v[pidx].y);
             }
-            if(WIN)
-            {
 #pragma unroll
-                for(int pidx = 0; pidx < 32; ++pidx)
-                {
-                    const float2 w = s_win[lane + 32 * pidx];
-                    v[pidx].x *= w.x;
-                    v[pidx].y *= w.y;
-                }
+            for(int pidx = 0; pidx < 32; ++pidx)
+            {
+                const float2 w = s_win[lane + 32 * pidx];
+                v[pidx].x *= w.x;
+                v[pidx].y *= w.y;
             }
             const bool nz = __any_sync(0xffffffffu, (nzbits & 0x7fffffffu) != 0u);
 
-            // ---- pass A: 32-point DFTs over n2, inter-pass twiddle, transpose through shared ----
-            dft_bitrev<32>(v);
-            __syncwarp(); // every lane has read the frame before the buffer becomes the transpose area
-#pragma unroll
-            for(int k2 = 0; k2 < 32; ++k2)
+            // ---- two radix-32 register passes sharing one copy of the butterfly code ----
+#pragma unroll 1
+            for(int pass = 0; pass < 2; ++pass)
             {
-                float2 a = v[bitrev<32>(k2)];
-                if(k2 > 0)
-                    a = cmul(a, s_twA[k2 * 32 + lane]);
-                buf[lane * 33 + k2] = a;
-            }
-            __syncwarp();
-#pragma unroll
-            for(int n1 = 0; n1 < 32; ++n1)
-                v[n1] = buf[n1 * 33 + lane];
-            // ---- pass B: 32-point DFTs over n1 -> X[lane + 32 k1] in v[bitrev(k1)] ----
-            dft_bitrev<32>(v);
-
-            // ---- split pass on pairs (k, 1024-k): upper half goes to the partner lane ----
-            __syncwarp();
-#pragma unroll
-            for(int q = 16; q < 32; ++q)
-                buf[(q - 16) * 32 + lane] = v[bitrev<32>(q)];
-            if(lane == 0)
-                buf[16 * 32] = v[0]; // X[0] doubles as "X[1024]" for the k = 0 pair
-            __syncwarp();
-            float mag1[16], mag2[16];
-#pragma unroll
-            for(int q = 0; q < 16; ++q)
-            {
-                const float2 a = v[bitrev<32>(q)];
-                float2 b = buf[(15 - q) * 32 + pbase];
-                b.y = -b.y;
-                const float2 sum = cadd(a, b);
-                const float2 dif = csub(a, b);
-                const float2 o = make_float2(dif.y, -dif.x);
-                const float2 wo = cmul(o, s_twP[q * 32 + lane]);
-                const float2 y1 = cadd(sum, wo);
-                const float2 y2 = csub(sum, wo);
-                float p1 = fmaf(y1.x, y1.x, y1.y * y1.y);
-                float p2 = fmaf(y2.x, y2.x, y2.y * y2.y);
-                if(q == 0)
+                dft_bitrev<32>(v);
+                if(pass == 0)
                 {
-                    // lane 0: the pair (0, 1024) has no bin 1024; its second slot carries bin 512 = conj(X[512])
-                    const float2 x512 = v[bitrev<32>(16)];
-                    const float p512 = 4.0f * fmaf(x512.x, x512.x, x512.y * x512.y);
-                    p2 = (lane == 0) ? p512 : p2;
-                }
-                mag1[q] = sqrt_approx(p1) * p.coef_half;
-                mag2[q] = sqrt_approx(p2) * p.coef_half;
-            }
-            __syncwarp(); // all generic-proxy accesses to buf are done
-
-            // ---- prefetch the next frame (or the next stream's first frame) while the epilogue runs ----
-            if(lane == 0)
-            {
-                const float *next = nullptr;
-                if(t + 1 < T)
-                    next = pcm_s + (size_t)(t + 1) * p.hop;
-                else if(s + total_warps < S)
-                    next = p.pcm + (size_t)(s + total_warps) * p.stream_stride;
-                if(next != nullptr)
-                {
-                    fence_proxy_async();
-                    mbar_expect_tx(mbar, kN * 4);
-                    tma_load_1d(buf, next, kN * 4, mbar);
+                    // inter-pass twiddle W_1024^(n1 k2), then transpose through the (padded) shared buffer
+                    __syncwarp(); // every lane has read the frame before the buffer becomes the transpose area
+#pragma unroll
+                    for(int k2 = 0; k2 < 32; ++k2)
+                    {
+                        float2 a = v[bitrev<32>(k2)];
+                        if(k2 > 0)
+                            a = cmul(a, s_twA[k2 * 32 + lane]);
+                        buf[lane * 33 + k2] = a;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for(int n1 = 0; n1 < 32; ++n1)
+                        v[n1] = buf[n1 * 33 + lane];
+                    __syncwarp(); // all generic-proxy accesses to buf are done: it can take the next frame
+                    // prefetch the next frame (or the next stream's first frame) under pass B + epilogue
+                    if(lane == 0)
+                    {
+                        const float *next = nullptr;
+                        if(t + 1 < T)
+                            next = pcm_s + (size_t)(t + 1) * p.hop;
+                        else if(s + total_warps < S)
+                            next = p.pcm + (size_t)(s + total_warps) * p.stream_stride;
+                        if(next != nullptr)
+                        {
+                            fence_proxy_async();
+                            mbar_expect_tx(mbar, kN * 4);
+                            tma_load_1d(buf, next, kN * 4, mbar);
+                        }
+                    }
                 }
             }
+            // now X[lane + 32 k1] = v[bitrev(k1)]
 
+            // The split pass needs X[1024-k] next to X[k]: lane j fetches the upper half of lane (32-j)%32 by
+            // warp shuffle (lane 0 pairs within its own registers, one index higher).
             // ---- gate (src/source_generic.cpp:63-95), single capture channel ----
             const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
             bool do_proc = !skip_all;
@@ -262,88 +248,119 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
                 }
             }
 
-            // ---- slope, EMA (src/source_generic.cpp:121-134) ----
-            if(do_proc)
-            {
-#pragma unroll
-                for(int q = 0; q < 16; ++q)
-                {
-                    float m1 = mag1[q], m2 = mag2[q];
-                    if(EXTRA && p.slope != nullptr)
-                    {
-                        m1 *= __ldg(p.slope + lane + 32 * q);
-                        m2 *= __ldg(p.slope + ((q == 0) ? k2_q0 : (kb + 32 * (31 - q))));
-                    }
-                    if(TSM)
-                    {
-                        float o1 = st1[q], o2 = st2[q];
-                        if(EXTRA && p.fast_peaks)
-                        {
-                            o1 = fmaxf(m1, o1);
-                            o2 = fmaxf(m2, o2);
-                        }
-                        m1 = __fadd_rn(__fmul_rn(p.g, o1), __fmul_rn(p.g2, m1));
-                        m2 = __fadd_rn(__fmul_rn(p.g, o2), __fmul_rn(p.g2, m2));
-                    }
-                    st1[q] = m1;
-                    st2[q] = m2;
-                }
-            }
-
-            // ---- dBFS, volume normalisation, roll-off, store (src/source_generic.cpp:138-179) ----
+            float *odb = p.out_db + ((size_t)s * T + t) * B;
             float vc = 0.0f;
             if(EXTRA && p.normalize)
             {
                 const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + t] : 0.0f;
                 vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
             }
-            float *odb = p.out_db + ((size_t)s * T + t) * B;
-            const float *prev_db = (t > 0) ? (odb - B) : hold_s;
             bool outs = true;
             float peak = -INFINITY;
-#pragma unroll
-            for(int q = 0; q < 16; ++q)
+
+            if(do_proc && !last_silent)
             {
-                const int k1 = lane + 32 * q;
-                const int k2 = (q == 0) ? k2_q0 : (kb + 32 * (31 - q));
-                float o1, o2;
-                if(last_silent)
+                // ---- hot path: split pass -> |X| -> slope -> EMA -> dBFS -> (volume, roll-off) -> store ----
+#pragma unroll
+                for(int q = 0; q < 16; ++q)
                 {
-                    o1 = prev_db[k1];
-                    o2 = prev_db[k2];
-                }
-                else
-                {
-                    const float in1 = do_proc ? st1[q] : prev_db[k1];
-                    const float in2 = do_proc ? st2[q] : prev_db[k2];
-                    o1 = dbfs_fast(in1, p.db_min);
-                    o2 = dbfs_fast(in2, p.db_min);
+                    const int k1 = lane + 32 * q;
+                    const int k2 = (q == 0) ? k2_q0 : (kb + 32 * (31 - q));
+                    const float2 a = v[bitrev<32>(q)];
+                    float2 bp;
+                    bp.x = __shfl_sync(0xffffffffu, v[bitrev<32>(31 - q)].x, jp);
+                    bp.y = __shfl_sync(0xffffffffu, v[bitrev<32>(31 - q)].y, jp);
+                    if(lane == 0)
+                        bp = v[bitrev<32>((32 - q) & 31)];
+                    const float2 b = make_float2(bp.x, -bp.y);
+                    const float2 sum = cadd(a, b);
+                    const float2 dif = csub(a, b);
+                    const float2 o = make_float2(dif.y, -dif.x);
+                    const float2 wo = cmul(o, s_twP[q * 32 + lane]);
+                    const float2 y1 = cadd(sum, wo);
+                    const float2 y2 = csub(sum, wo);
+                    float p1 = fmaf(y1.x, y1.x, y1.y * y1.y);
+                    float p2 = fmaf(y2.x, y2.x, y2.y * y2.y);
+                    if(q == 0)
+                    {
+                        // lane 0: the pair (0, 1024) has no bin 1024; its second slot carries bin 512 = conj(X[512])
+                        const float2 x512 = v[bitrev<32>(16)];
+                        const float p512 = 4.0f * fmaf(x512.x, x512.x, x512.y * x512.y);
+                        p2 = (lane == 0) ? p512 : p2;
+                    }
+                    float m1 = sqrt_approx(p1), m2 = sqrt_approx(p2);
+                    if(EXTRA && p.slope != nullptr)
+                    {
+                        m1 *= __ldg(p.slope + k1);
+                        m2 *= __ldg(p.slope + k2);
+                    }
+                    if(TSM)
+                    {
+                        const float2 old = sst[q * 32];
+                        float o1 = old.x, o2 = old.y;
+                        if(EXTRA && p.fast_peaks)
+                        {
+                            o1 = fmaxf(m1, o1);
+                            o2 = fmaxf(m2, o2);
+                        }
+                        // g*old + g2*new with one fused rounding, as the reference's AVX2 path (src/source_avx2.cpp:154)
+                        m1 = fmaf(p.g, o1, p.g2 * m1);
+                        m2 = fmaf(p.g, o2, p.g2 * m2);
+                    }
+                    sst[q * 32] = make_float2(m1, m2);
+                    float d1 = dbfs_fast(m1, p.db_min);
+                    float d2 = dbfs_fast(m2, p.db_min);
                     if(EXTRA)
                     {
                         if(p.normalize)
                         {
                             if(k1 >= 1)
-                                o1 += vc;
-                            o2 += vc;
+                                d1 += vc;
+                            d2 += vc;
                         }
                         if(p.rolloff != nullptr)
                         {
                             if(k1 >= 1)
-                                o1 = fmaxf(o1 - __ldg(p.rolloff + k1), p.db_min);
-                            o2 = fmaxf(o2 - __ldg(p.rolloff + k2), p.db_min);
+                                d1 = fmaxf(d1 - __ldg(p.rolloff + k1), p.db_min);
+                            d2 = fmaxf(d2 - __ldg(p.rolloff + k2), p.db_min);
+                        }
+                        if(k1 >= 1)
+                            peak = fmaxf(peak, d1);
+                        peak = fmaxf(peak, d2);
+                    }
+                    if(GATE)
+                        outs &= !(d1 > p.floor_m10) & !(d2 > p.floor_m10);
+                    stg_stream(odb + k1, d1);
+                    stg_stream(odb + k2, d2);
+                }
+                last_from_state = true;
+            }
+            else
+            {
+                // ---- rare path: tick returned early (hold, src/source_generic.cpp:138-139) or the channel was
+                //      skipped while the tick went on (stale dB re-converted) ----
+                const float *prev_db = (t > 0) ? (odb - B) : hold_s;
+#pragma unroll 1
+                for(int k = lane; k < B; k += 32)
+                {
+                    float o = prev_db[k];
+                    if(!last_silent)
+                    {
+                        o = dbfs(o, p.db_min);
+                        if(EXTRA && k >= 1)
+                        {
+                            if(p.normalize)
+                                o += vc;
+                            if(p.rolloff != nullptr)
+                                o = fmaxf(o - __ldg(p.rolloff + k), p.db_min);
                         }
                     }
+                    outs &= !(o > p.floor_m10);
+                    if(k >= 1)
+                        peak = fmaxf(peak, o);
+                    odb[k] = o;
                 }
-                if(GATE)
-                    outs &= !(o1 > p.floor_m10) & !(o2 > p.floor_m10);
-                if(EXTRA)
-                {
-                    if(k1 >= 1)
-                        peak = fmaxf(peak, o1);
-                    peak = fmaxf(peak, o2);
-                }
-                stg_stream(odb + k1, o1);
-                stg_stream(odb + k2, o2);
+                last_from_state = false;
             }
             if(GATE && !last_silent)
                 prev_out_silent = __all_sync(0xffffffffu, outs);
@@ -360,26 +377,37 @@ __global__ void __launch_bounds__(fast::kThreads, 2) stft2048_fast_kernel(const 
             }
         }
 
-        // ---- state back to the engine ----
+        // ---- state back to the engine; m_decibels mirror for the next call's gate / hold paths ----
         {
             float *sp = p.state + (size_t)s * B;
             const float *last = p.out_db + ((size_t)s * T + (T - 1)) * B;
+            const bool plain = !EXTRA || (!p.normalize && p.rolloff == nullptr);
 #pragma unroll
             for(int q = 0; q < 16; ++q)
             {
                 const int k1 = lane + 32 * q;
                 const int k2 = (q == 0) ? k2_q0 : (kb + 32 * (31 - q));
-                sp[k1] = st1[q];
-                sp[k2] = st2[q];
+                const float2 stv = sst[q * 32];
+                sp[k1] = stv.x;
+                sp[k2] = stv.y;
                 if(p.write_hold)
                 {
-                    hold_s[k1] = last[k1];
-                    hold_s[k2] = last[k2];
+                    if(last_from_state && plain)
+                    {
+                        hold_s[k1] = dbfs_fast(stv.x, p.db_min); // identical to what the last tick stored
+                        hold_s[k2] = dbfs_fast(stv.y, p.db_min);
+                    }
+                    else
+                    {
+                        hold_s[k1] = last[k1];
+                        hold_s[k2] = last[k2];
+                    }
                 }
             }
             if(lane == 0)
                 p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent ? 2u : 0u) | 4u);
         }
+        __syncwarp();
     }
 }
 
