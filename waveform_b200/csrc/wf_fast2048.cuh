@@ -79,16 +79,18 @@ __device__ __forceinline__ float lg2_approx_ftz(float x)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// dbfs (src/source.hpp:293-299) on the MUFU.LG2 path: 20 log10(m) = (20 log10 2) log2(m).
-// Normal magnitudes take 3 instructions; zero / subnormal magnitudes (digital silence, the far tail of an EMA
-// decay) take the rare branch, which rescales so that subnormals are still converted exactly like log10f would.
-__device__ __forceinline__ float dbfs_fast(float mag, float db_min)
+// dbfs (src/source.hpp:293-299) on the MUFU.LG2 path: 20 log10(m) = (20 log10 2) log2(m), two bins at a time.
+// Magnitudes below FLT_MIN (digital silence, the far tail of an EMA decay: < -758.6 dBFS) report DB_MIN —
+// the reference reports DB_MIN for exact zero and a value below DB_MIN for subnormals; this kernel clamps
+// those to DB_MIN (the generic kernel keeps the exact behaviour).  See DESIGN.md §Parity.
+__device__ __forceinline__ pk::c64 dbfs2(float m1, float m2, float db_min)
 {
     constexpr float k = 6.02059991327962390f; // 20 log10(2)
-    float o = lg2_approx_ftz(mag) * k;
-    if(mag < 1.17549435e-38f)
-        o = (mag > 0.0f) ? (lg2_approx_ftz(mag * 16777216.0f) - 24.0f) * k : db_min;
-    return o;
+    pk::c64 d = pk::mul(pk::make(lg2_approx_ftz(m1), lg2_approx_ftz(m2)), pk::make(k, k));
+    // lg2.approx.ftz(x < FLT_MIN) = -inf and 20 log10(FLT_MIN) == DB_MIN, so the clamp is one max per bin
+    float d1, d2;
+    pk::split(d, d1, d2);
+    return pk::make(fmaxf(d1, db_min), fmaxf(d2, db_min));
 }
 
 } // namespace fast
@@ -169,28 +171,26 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             // ---- frame from shared (TMA-staged), window in the load prologue ----
             mbar_wait(mbar, phase);
             phase ^= 1u;
-            float2 v[32];
-            unsigned nzbits = 0;
+            pk::c64 v[32];
+            unsigned long long nzbits = 0;
+            const pk::c64 *buf64 = reinterpret_cast<const pk::c64 *>(buf);
+            const pk::c64 *win64 = reinterpret_cast<const pk::c64 *>(s_win);
 #pragma unroll
             for(int pidx = 0; pidx < 32; ++pidx)
             {
-                v[pidx] = buf[lane + 32 * pidx];
-                nzbits |= __float_as_uint(v[pidx].x) | __float_as_uint(v[pidx].y);
+                v[pidx] = buf64[lane + 32 * pidx];
+                nzbits |= v[pidx];
             }
 #pragma unroll
             for(int pidx = 0; pidx < 32; ++pidx)
-            {
-                const float2 w = s_win[lane + 32 * pidx];
-                v[pidx].x *= w.x;
-                v[pidx].y *= w.y;
-            }
-            const bool nz = __any_sync(0xffffffffu, (nzbits & 0x7fffffffu) != 0u);
+                v[pidx] = pk::mul(v[pidx], win64[lane + 32 * pidx]);
+            const bool nz = __any_sync(0xffffffffu, (nzbits & 0x7fffffff7fffffffull) != 0ull);
 
             // ---- two radix-32 register passes sharing one copy of the butterfly code ----
 #pragma unroll 1
             for(int pass = 0; pass < 2; ++pass)
             {
-                dft_bitrev<32>(v);
+                pk::dft_bitrev<32>(v);
                 if(pass == 0)
                 {
                     // inter-pass twiddle W_1024^(n1 k2), then transpose through the (padded) shared buffer
@@ -198,15 +198,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
 #pragma unroll
                     for(int k2 = 0; k2 < 32; ++k2)
                     {
-                        float2 a = v[bitrev<32>(k2)];
+                        pk::c64 a = v[bitrev<32>(k2)];
                         if(k2 > 0)
-                            a = cmul(a, s_twA[k2 * 32 + lane]);
-                        buf[lane * 33 + k2] = a;
+                            a = pk::cmul(a, reinterpret_cast<const pk::c64 *>(s_twA)[k2 * 32 + lane]);
+                        reinterpret_cast<pk::c64 *>(buf)[lane * 33 + k2] = a;
                     }
                     __syncwarp();
 #pragma unroll
                     for(int n1 = 0; n1 < 32; ++n1)
-                        v[n1] = buf[n1 * 33 + lane];
+                        v[n1] = buf64[n1 * 33 + lane];
                     __syncwarp(); // all generic-proxy accesses to buf are done: it can take the next frame
                     // prefetch the next frame (or the next stream's first frame) under pass B + epilogue
                     if(lane == 0)
@@ -266,50 +266,42 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                 {
                     const int k1 = lane + 32 * q;
                     const int k2 = (q == 0) ? k2_q0 : (kb + 32 * (31 - q));
-                    const float2 a = v[bitrev<32>(q)];
-                    float2 bp;
-                    bp.x = __shfl_sync(0xffffffffu, v[bitrev<32>(31 - q)].x, jp);
-                    bp.y = __shfl_sync(0xffffffffu, v[bitrev<32>(31 - q)].y, jp);
+                    const pk::c64 a = v[bitrev<32>(q)];
+                    unsigned long long bp = __shfl_sync(0xffffffffu, v[bitrev<32>(31 - q)], jp);
                     if(lane == 0)
                         bp = v[bitrev<32>((32 - q) & 31)];
-                    const float2 b = make_float2(bp.x, -bp.y);
-                    const float2 sum = cadd(a, b);
-                    const float2 dif = csub(a, b);
-                    const float2 o = make_float2(dif.y, -dif.x);
-                    const float2 wo = cmul(o, s_twP[q * 32 + lane]);
-                    const float2 y1 = cadd(sum, wo);
-                    const float2 y2 = csub(sum, wo);
-                    float p1 = fmaf(y1.x, y1.x, y1.y * y1.y);
-                    float p2 = fmaf(y2.x, y2.x, y2.y * y2.y);
+                    const pk::c64 b = pk::conj(bp);
+                    const pk::c64 sum = pk::add(a, b);
+                    const pk::c64 o = pk::mul_neg_i(pk::sub(a, b));
+                    const pk::c64 wo = pk::cmul(o, reinterpret_cast<const pk::c64 *>(s_twP)[q * 32 + lane]);
+                    const pk::c64 y1 = pk::add(sum, wo);
+                    const pk::c64 y2 = pk::sub(sum, wo);
+                    const pk::c64 s1 = pk::mul(y1, y1), s2 = pk::mul(y2, y2);
+                    float p1 = pk::re(s1) + pk::im(s1);
+                    float p2 = pk::re(s2) + pk::im(s2);
                     if(q == 0)
                     {
                         // lane 0: the pair (0, 1024) has no bin 1024; its second slot carries bin 512 = conj(X[512])
-                        const float2 x512 = v[bitrev<32>(16)];
-                        const float p512 = 4.0f * fmaf(x512.x, x512.x, x512.y * x512.y);
+                        const pk::c64 x512 = v[bitrev<32>(16)];
+                        const pk::c64 sq = pk::mul(x512, x512);
+                        const float p512 = 4.0f * (pk::re(sq) + pk::im(sq));
                         p2 = (lane == 0) ? p512 : p2;
                     }
-                    float m1 = sqrt_approx(p1), m2 = sqrt_approx(p2);
+                    pk::c64 m = pk::make(sqrt_approx(p1), sqrt_approx(p2)); // (|X[k1]|, |X[k2]|), normalised via the window
                     if(EXTRA && p.slope != nullptr)
-                    {
-                        m1 *= __ldg(p.slope + k1);
-                        m2 *= __ldg(p.slope + k2);
-                    }
+                        m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + k2)));
+                    pk::c64 *sst64 = reinterpret_cast<pk::c64 *>(sst);
                     if(TSM)
                     {
-                        const float2 old = sst[q * 32];
-                        float o1 = old.x, o2 = old.y;
+                        pk::c64 old = sst64[q * 32];
                         if(EXTRA && p.fast_peaks)
-                        {
-                            o1 = fmaxf(m1, o1);
-                            o2 = fmaxf(m2, o2);
-                        }
+                            old = pk::make(fmaxf(pk::re(m), pk::re(old)), fmaxf(pk::im(m), pk::im(old)));
                         // g*old + g2*new with one fused rounding, as the reference's AVX2 path (src/source_avx2.cpp:154)
-                        m1 = fmaf(p.g, o1, p.g2 * m1);
-                        m2 = fmaf(p.g, o2, p.g2 * m2);
+                        m = pk::fma(pk::make(p.g, p.g), old, pk::mul(pk::make(p.g2, p.g2), m));
                     }
-                    sst[q * 32] = make_float2(m1, m2);
-                    float d1 = dbfs_fast(m1, p.db_min);
-                    float d2 = dbfs_fast(m2, p.db_min);
+                    sst64[q * 32] = m;
+                    float d1, d2;
+                    pk::split(dbfs2(pk::re(m), pk::im(m), p.db_min), d1, d2);
                     if(EXTRA)
                     {
                         if(p.normalize)
@@ -394,8 +386,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                 {
                     if(last_from_state && plain)
                     {
-                        hold_s[k1] = dbfs_fast(stv.x, p.db_min); // identical to what the last tick stored
-                        hold_s[k2] = dbfs_fast(stv.y, p.db_min);
+                        float h1, h2;
+                        pk::split(dbfs2(stv.x, stv.y, p.db_min), h1, h2); // identical to what the last tick stored
+                        hold_s[k1] = h1;
+                        hold_s[k2] = h2;
                     }
                     else
                     {

@@ -135,3 +135,144 @@ __device__ __forceinline__ void dft_bitrev(float2 (&v)[R])
 }
 
 } // namespace wf
+
+// ---------------------------------------------------------------------------------------------------
+// Packed complex arithmetic on Blackwell's f32x2 datapath (add/mul/fma.rn.f32x2 -> FADD2/FMUL2/FFMA2).
+// A complex number lives in one 64-bit register pair (re = low half, im = high half).  The SASS operand
+// modifiers (.F32x2.LO_HI, .NP/.PN) make swap / conj / multiply-by-±i free, so a complex add is ONE
+// instruction and a complex multiply is TWO (vs 2 and 4 scalar) — the kernels here are issue-bound, not
+// FP-pipe-bound (tools/ubench/f32x2.cu: FFMA2 has the same FMA/clk as FFMA but half the issue slots).
+// ---------------------------------------------------------------------------------------------------
+namespace wf {
+namespace pk {
+
+typedef unsigned long long c64;
+
+__device__ __forceinline__ c64 make(float re, float im)
+{
+    c64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im));
+    return r;
+}
+__device__ __forceinline__ void split(c64 a, float &re, float &im)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(a));
+}
+__device__ __forceinline__ float re(c64 a)
+{
+    float x, y;
+    split(a, x, y);
+    return x;
+}
+__device__ __forceinline__ float im(c64 a)
+{
+    float x, y;
+    split(a, x, y);
+    return y;
+}
+__device__ __forceinline__ c64 from(float2 a) { return make(a.x, a.y); }
+__device__ __forceinline__ float2 to_float2(c64 a)
+{
+    float2 r;
+    split(a, r.x, r.y);
+    return r;
+}
+__device__ __forceinline__ c64 add(c64 a, c64 b)
+{
+    c64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 sub(c64 a, c64 b)
+{
+    c64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 mul(c64 a, c64 b) // elementwise
+{
+    c64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ c64 fma(c64 a, c64 b, c64 c) // elementwise a*b+c
+{
+    c64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ c64 swap(c64 a)
+{
+    float x, y;
+    split(a, x, y);
+    return make(y, x);
+}
+__device__ __forceinline__ c64 conj(c64 a)
+{
+    float x, y;
+    split(a, x, y);
+    return make(x, -y);
+}
+__device__ __forceinline__ c64 mul_neg_i(c64 a) // a * (-i) = (im, -re)
+{
+    float x, y;
+    split(a, x, y);
+    return make(y, -x);
+}
+// complex multiply by a run-time twiddle w = (c, s):  a*(c,c) + (-a.im, a.re)*(s,s).
+// In this form ptxas emits exactly FMUL2 + FFMA2 (broadcast .F32 operands, .LO_HI.NP on the A operand).
+__device__ __forceinline__ c64 cmul(c64 a, c64 w)
+{
+    float x, y, c, s;
+    split(a, x, y);
+    split(w, c, s);
+    return fma(make(-y, x), make(s, s), mul(a, make(c, c)));
+}
+
+// multiply by the compile-time twiddle W_L^J = exp(-2 pi i J / L)
+template<int J, int L>
+__device__ __forceinline__ c64 mul_tw(c64 a)
+{
+    if constexpr(J == 0)
+        return a;
+    else if constexpr(4 * J == L)
+        return mul_neg_i(a);
+    else
+    {
+        constexpr float c = (float)cx::cos2pi(J, L);
+        constexpr float s = -(float)cx::sin2pi(J, L);
+        return fma(swap(a), make(-s, s), mul(a, make(c, c)));
+    }
+}
+
+template<int L, int BASE, int J, int R>
+__device__ __forceinline__ void dif_bfly(c64 (&v)[R])
+{
+    if constexpr(J < L / 2)
+    {
+        const c64 a = v[BASE + J];
+        const c64 c = v[BASE + J + L / 2];
+        v[BASE + J] = add(a, c);
+        v[BASE + J + L / 2] = mul_tw<J, L>(sub(a, c));
+        dif_bfly<L, BASE, J + 1, R>(v);
+    }
+}
+template<int L, int BASE, int R>
+__device__ __forceinline__ void dif_block(c64 (&v)[R])
+{
+    if constexpr(L >= 2)
+    {
+        dif_bfly<L, BASE, 0, R>(v);
+        dif_block<L / 2, BASE, R>(v);
+        dif_block<L / 2, BASE + L / 2, R>(v);
+    }
+}
+// In-place forward DFT of v[0..R): afterwards X[k] == v[bitrev<R>(k)].
+template<int R>
+__device__ __forceinline__ void dft_bitrev(c64 (&v)[R])
+{
+    dif_block<R, 0, R>(v);
+}
+
+} // namespace pk
+} // namespace wf
