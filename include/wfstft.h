@@ -163,6 +163,11 @@ int64_t wf_get_table(const wf_engine *e, int which, float *out, int64_t capacity
 /* ≙ WAVSource::get_gravity(seconds), src/source.hpp:301-312. */
 float wf_gravity(const wf_engine *e, float seconds);
 
+/* The same setup-time tables, computed from a config WITHOUT creating an engine (no device needed): lets a host
+ * (or a CPU-only test) check them against the plugin's own m_* tables.  Returns element count or a negative status;
+ * info (optional) receives the derived facts (device/sm_count = -1). */
+int64_t wf_preview_table(const wf_config *cfg, int which, float *out, int64_t capacity, wf_info *info);
+
 /* ≙ tick_spectrum for every (stream, tick) of the batch (+ render-time interpolation when out_points is set).
  * Blocking: returns after results are in the caller's buffers. */
 int wf_process(wf_engine *e, const wf_batch *batch);

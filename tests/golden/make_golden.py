@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Generate golden input/output vectors from the UNMODIFIED reference compiled into oracle/_ref
+(make -C oracle/ref_build).  Run in the dev container where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Each case_*.npz holds: settings (json), channels, hop, pcm [cc, samples] float32, and what the reference's
+WAVSourceGeneric produced tick by tick: db [T, dch, B], points [T, dch, P] (generic interpolation path),
+silent [T], plus the tables WAVSource::update() built (window, slope, rolloff, interp indices / weights / band widths).
+The PCM is stored (not regenerated) so the fixtures do not depend on any RNG implementation.
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from helpers import synth_pcm  # noqa: E402
+from oracle.refbind import IMPL_GENERIC, RefSource  # noqa: E402
+
+OUT = Path(__file__).resolve().parent
+
+CASES = {
+    # BASELINE.json configs[0]: 1 mono channel, N=1024 Hann, bars mode, generic CPU path
+    "c1_mono_1024_hann_bars": dict(settings={"fft_size": 1024, "window": "hann", "display_mode": "bars",
+                                             "interp_mode": "catmull_rom"}, channels=1, T=12, hop=800),
+    # configs[1] shape: stereo, N=4096 Blackman-Harris, dBFS + temporal smoothing, 60 fps hop
+    "c2_stereo_4096_bh": dict(settings={"fft_size": 4096, "window": "blackman_harris", "channel_mode": "stereo"},
+                              channels=2, T=8, hop=800),
+    # configs[2] shape: mono N=2048 Hann EMA dB
+    "c3_mono_2048_hann": dict(settings={"fft_size": 2048, "window": "hann"}, channels=1, T=10, hop=2048),
+    # configs[3] shape (scaled down): 75 % overlap, log-frequency Lanczos curve
+    "c4_mono_2048_overlap_lanczos": dict(settings={"fft_size": 2048, "window": "hann", "interp_mode": "lanczos",
+                                                   "width": 400}, channels=1, T=10, hop=512),
+    # everything on: slope, roll-off, fast peaks, gaussian, 2ch->mono mix, volume normalisation
+    "mix_1024_all_options": dict(settings={"fft_size": 1024, "window": "hamming", "slope": 0.75, "rolloff_q": 1.5,
+                                           "rolloff_rate": 9.0, "fast_peaks": True, "filter_mode": "gauss",
+                                           "filter_radius": 2.0, "interp_mode": "lanczos", "width": 256,
+                                           "normalize_volume": True}, channels=2, T=10, hop=512, rms=True),
+    # silence gate: decay, freeze, wake-up
+    "gate_1024_silence": dict(settings={"fft_size": 1024, "window": "hann", "gravity": 0.3, "floor": -40},
+                              channels=1, T=40, hop=1024, silence=(4, 30)),
+    # non-power-of-two size the plugin's auto mode produces at 48 kHz / 60 fps (src/source.cpp:1161-1167)
+    "auto_800_tvexp": dict(settings={"fft_size": 800, "window": "blackman", "temporal_smoothing": "tv_exp_moving_avg",
+                                     "gravity": 0.5, "log_scale": False, "interp_mode": "point", "width": 200},
+                           channels=1, T=8, hop=800),
+}
+
+
+def main():
+    for name, c in CASES.items():
+        ref = RefSource(c["settings"], impl=IMPL_GENERIC, channels=c["channels"])
+        N, T, hop = ref.fft_size, c["T"], c["hop"]
+        cc = ref.capture_channels
+        pcm = synth_pcm(1, cc, (T - 1) * hop + N, seed=0xB200 + len(name))[0]
+        if "silence" in c:
+            a, b = c["silence"]
+            pcm[:, a * hop:] = 0.0
+            pcm[:, b * hop: (b + 2) * hop] = 0.05
+        rms = None
+        if c.get("rms"):
+            rms = (0.02 + 0.3 * np.random.default_rng(7).uniform(size=T)).astype(np.float32)
+        r = ref.run_stft(pcm, T, hop, seconds=1.0 / 60.0, rms=rms, want_points=True, fma3=False)
+        taps, weights = ref.interp_kernel()
+        gk, gr, gs = ref.gauss_kernel()
+        np.savez_compressed(
+            OUT / f"case_{name}.npz",
+            settings=json.dumps(c["settings"]), channels=c["channels"], hop=hop, n_frames=T, seconds=1.0 / 60.0,
+            pcm=pcm, rms=rms if rms is not None else np.zeros(0, np.float32),
+            db=r["db"], points=r["points"], silent=r["silent"],
+            window=ref.window() if ref.window() is not None else np.zeros(0, np.float32),
+            window_sum=np.float32(ref.window_sum),
+            slope=ref.slope() if ref.slope() is not None else np.zeros(0, np.float32),
+            rolloff=ref.rolloff() if ref.rolloff() is not None else np.zeros(0, np.float32),
+            interp_indices=ref.interp_indices(), band_widths=ref.band_widths(),
+            interp_weights=weights if weights is not None else np.zeros((0, 0), np.float32),
+            gauss=gk, gauss_sum=np.float32(gs), db_min=np.float32(ref.db_min),
+        )
+        print(name, "N", N, "db", r["db"].shape, "points", r["points"].shape, "silent ticks", int(r["silent"].sum()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""CPU-only checks of the product's C-ABI: the library loads, exports every symbol include/wfstft.h declares,
+struct layouts match the header, host-side tables equal the reference's, and without a GPU it FAILS LOUDLY
+(no CPU fallback)."""
+import ctypes as C
+import json
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from waveform_b200.engine import EXPORTS, load_library
+
+    hdr = (ROOT / "include" / "wfstft.h").read_text()
+    declared = sorted(set(re.findall(r"\b(wf_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "header parse failed"
+    L = load_library()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in wfstft.h but not exported"
+    assert sorted(EXPORTS) == declared
+    assert L.wf_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from waveform_b200.engine import WfBatch, WfConfig, WfInfo
+
+    src = tmp_path / "sz.c"
+    src.write_text('#include "wfstft.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(wf_config), sizeof(wf_batch), sizeof(wf_info),'
+                   'offsetof(wf_batch,pcm), offsetof(wf_batch,out_peak), offsetof(wf_config,filter_radius));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [C.sizeof(WfConfig), C.sizeof(WfBatch), C.sizeof(WfInfo), WfBatch.pcm.offset,
+                                    WfBatch.out_peak.offset, WfConfig.filter_radius.offset]
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    from waveform_b200 import Engine, WfError
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(WfError) as ei:
+        Engine({"fft_size": 2048}, channels=1)
+    assert ei.value.status == -4
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_config_defaults_are_the_plugin_defaults():
+    from waveform_b200.engine import WfConfig, load_library
+
+    c = WfConfig()
+    load_library().wf_config_init(C.byref(c))
+    # src/source.cpp:119-174
+    assert (c.fft_size, c.window, c.tsmoothing, c.interp_mode, c.filter_mode) == (4096, 1, 1, 2, 0)
+    assert abs(c.gravity - 0.65) < 1e-7 and (c.cutoff_low, c.cutoff_high, c.floor_db, c.ceiling_db) == (30, 17500, -65, 0)
+    assert (c.width, c.bar_width, c.bar_gap, c.log_scale) == (800, 24, 6, 1) and c.struct_size == C.sizeof(WfConfig)
+
+
+def test_unsupported_and_invalid_configs_are_errors():
+    from waveform_b200.engine import WfError, make_config, preview_tables
+
+    cfg = make_config({"fft_size": 2048}, channels=3)
+    assert cfg.capture_channels == 2                      # the plugin captures at most two (src/source.cpp:1089)
+    cfg.capture_channels = 3
+    with pytest.raises(WfError) as ei:
+        preview_tables(cfg)
+    assert ei.value.status == -1
+    cfg = make_config({"fft_size": 100}, channels=1)      # clamped like get_settings (src/source.cpp:562-565)
+    assert preview_tables(cfg)["info"].fft_size == 128
+    cfg = make_config({"fft_size": 2050}, channels=1)
+    assert preview_tables(cfg)["info"].fft_size == 2048
+    with pytest.raises(KeyError):
+        make_config({"render_mode": "solid"})             # display plumbing is outside the hot path
+
+
+GOLD = sorted((ROOT / "tests" / "golden").glob("case_*.npz"))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_engine_host_tables_equal_reference_tables(path):
+    """libwfstft's setup-time tables (wf_tables.cpp) are bit-identical to what WAVSource::update() built."""
+    from waveform_b200.engine import make_config, preview_tables
+
+    z = np.load(path, allow_pickle=False)
+    settings = json.loads(str(z["settings"]))
+    t = preview_tables(make_config(settings, channels=int(z["channels"])))
+    for name in ("window", "slope", "rolloff", "interp_indices", "band_widths", "gauss"):
+        assert np.array_equal(t[name], z[name].ravel()), name
+    assert np.array_equal(t["interp_weights"], z["interp_weights"].ravel())
+    assert np.float32(t["info"].window_sum) == z["window_sum"]
+    assert np.float32(t["info"].db_min) == z["db_min"]
+    assert t["info"].bins == z["db"].shape[-1] and t["info"].num_points == z["points"].shape[-1]
+
+
+def test_product_never_imports_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    for f in list((ROOT / "waveform_b200").rglob("*.py")) + list((ROOT / "waveform_b200").rglob("*.c*")) \
+            + list((ROOT / "waveform_b200").rglob("*.h*")) + [ROOT / "include" / "wfstft.h"]:
+        txt = f.read_text(errors="ignore")
+        assert "oraclebind" not in txt and "refbind" not in txt and "wf_oracle" not in txt and "liboracle" not in txt, f
+    out = subprocess.run(["ldd", str(ROOT / "waveform_b200" / "lib" / "libwfstft.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "fftw" not in out.lower()

@@ -463,24 +463,14 @@ void wf_destroy(wf_engine *e)
     delete e;
 }
 
+static int64_t copy_table(const Tables &t, int which, float *out, int64_t capacity);
+static void fill_info(const Tables &t, wf_info *info, int device, int sm_count);
+
 int wf_get_info(const wf_engine *e, wf_info *info)
 {
     if(!e || !info)
         return WF_ERR_INVALID_ARG;
-    const Tables &t = e->tab;
-    info->fft_size = t.N;
-    info->bins = t.B;
-    info->capture_channels = t.cfg.capture_channels;
-    info->output_channels = t.output_channels;
-    info->display_channels = t.display_channels;
-    info->num_points = t.num_points;
-    info->num_bars = t.num_bars;
-    info->interp_taps = t.interp_taps;
-    info->n_interp_indices = (int32_t)t.interp_indices.size();
-    info->window_sum = t.window_sum;
-    info->db_min = t.db_min;
-    info->device = e->device;
-    info->sm_count = e->sm_count;
+    fill_info(e->tab, info, e->device, e->sm_count);
     return WF_OK;
 }
 
@@ -488,7 +478,13 @@ int64_t wf_get_table(const wf_engine *e, int which, float *out, int64_t capacity
 {
     if(!e)
         return WF_ERR_INVALID_ARG;
-    const Tables &t = e->tab;
+    return copy_table(e->tab, which, out, capacity);
+}
+
+float wf_gravity(const wf_engine *e, float seconds) { return e ? gravity_for(e->tab.cfg, seconds) : 0.0f; }
+
+static int64_t copy_table(const Tables &t, int which, float *out, int64_t capacity)
+{
     const void *src = nullptr;
     int64_t n = 0;
     switch(which)
@@ -511,7 +507,41 @@ int64_t wf_get_table(const wf_engine *e, int which, float *out, int64_t capacity
     return n;
 }
 
-float wf_gravity(const wf_engine *e, float seconds) { return e ? gravity_for(e->tab.cfg, seconds) : 0.0f; }
+static void fill_info(const Tables &t, wf_info *info, int device, int sm_count)
+{
+    info->fft_size = t.N;
+    info->bins = t.B;
+    info->capture_channels = t.cfg.capture_channels;
+    info->output_channels = t.output_channels;
+    info->display_channels = t.display_channels;
+    info->num_points = t.num_points;
+    info->num_bars = t.num_bars;
+    info->interp_taps = t.interp_taps;
+    info->n_interp_indices = (int32_t)t.interp_indices.size();
+    info->window_sum = t.window_sum;
+    info->db_min = t.db_min;
+    info->device = device;
+    info->sm_count = sm_count;
+}
+
+int64_t wf_preview_table(const wf_config *cfg, int which, float *out, int64_t capacity, wf_info *info)
+{
+    if(!cfg)
+        return WF_ERR_INVALID_ARG;
+    if(cfg->struct_size != sizeof(wf_config))
+        return WF_ERR_ABI;
+    Tables t;
+    const char *why = nullptr;
+    int rc = build_tables(*cfg, t, &why);
+    if(rc != WF_OK)
+    {
+        g_create_error = why ? why : "bad config";
+        return rc;
+    }
+    if(info)
+        fill_info(t, info, -1, -1);
+    return copy_table(t, which, out, capacity);
+}
 
 int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
 {

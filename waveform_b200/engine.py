@@ -40,7 +40,7 @@ TABLE_WINDOW, TABLE_SLOPE, TABLE_ROLLOFF, TABLE_INTERP_INDICES, TABLE_INTERP_WEI
 EXPORTS = [
     "wf_abi_version", "wf_strerror", "wf_last_error", "wf_config_init", "wf_create", "wf_destroy", "wf_get_info",
     "wf_get_table", "wf_gravity", "wf_process", "wf_process_async", "wf_synchronize", "wf_reset_state",
-    "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms",
+    "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_preview_table",
 ]
 
 
@@ -111,6 +111,8 @@ def load_library():
     L.wf_get_info.argtypes = [vp, C.POINTER(WfInfo)]
     L.wf_get_table.restype = C.c_int64
     L.wf_get_table.argtypes = [vp, C.c_int, vp, C.c_int64]
+    L.wf_preview_table.restype = C.c_int64
+    L.wf_preview_table.argtypes = [C.POINTER(WfConfig), C.c_int, vp, C.c_int64, C.POINTER(WfInfo)]
     L.wf_gravity.restype = C.c_float
     L.wf_gravity.argtypes = [vp, C.c_float]
     L.wf_process.argtypes = [vp, C.POINTER(WfBatch)]
@@ -168,6 +170,26 @@ def make_config(settings: dict | None = None, sample_rate: int = 48000, channels
         else:
             raise KeyError(f"setting {k!r} is outside the spectrum hot path")
     return c
+
+
+def preview_tables(cfg: WfConfig) -> dict:
+    """Host-side tables + derived facts for a config, without a device (wf_preview_table)."""
+    L = load_library()
+    info = WfInfo()
+    out = {}
+    names = {TABLE_WINDOW: "window", TABLE_SLOPE: "slope", TABLE_ROLLOFF: "rolloff",
+             TABLE_INTERP_INDICES: "interp_indices", TABLE_INTERP_WEIGHTS: "interp_weights",
+             TABLE_BAND_WIDTHS: "band_widths", TABLE_GAUSS: "gauss"}
+    for which, name in names.items():
+        n = L.wf_preview_table(C.byref(cfg), which, None, 0, C.byref(info))
+        if n < 0:
+            raise WfError(int(n), f"{L.wf_strerror(int(n)).decode()}: {L.wf_last_error(None).decode()}")
+        arr = np.zeros(n, dtype=np.int32 if which == TABLE_BAND_WIDTHS else np.float32)
+        if n:
+            L.wf_preview_table(C.byref(cfg), which, arr.ctypes.data, n, None)
+        out[name] = arr
+    out["info"] = info
+    return out
 
 
 def _ptr(x):
