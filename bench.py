@@ -310,7 +310,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                         "kernel": "stft_fused_kernel<2048,1>", "kernel_ms": kernel_ms,
+                         "kernel": "stft2048_fast_kernel<16,true,true,false> (csrc/wf_fast2048.cuh)", "kernel_ms": kernel_ms,
                          "bytes_per_launch": frames_per_gpu * BYTES_PER_FRAME},
             "cpu_baseline": cpu,
         }

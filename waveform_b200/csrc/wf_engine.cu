@@ -49,6 +49,10 @@ struct wf_engine {
     unsigned char *s_skip = nullptr, *s_silent = nullptr;
     size_t s_pcm_cap = 0, s_out_db_cap = 0, s_out_points_cap = 0, s_rms_cap = 0, s_peak_cap = 0, s_skip_cap = 0,
            s_silent_cap = 0;
+    // copy/compute pipeline for host-pointer batches
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t chunk_in[kMaxChunks] = {}, chunk_k[kMaxChunks] = {}, ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -454,6 +458,20 @@ void wf_destroy(wf_engine *e)
     for(void *p : ptrs)
         if(p)
             cudaFree(p);
+    for(auto ev : e->chunk_in)
+        if(ev)
+            cudaEventDestroy(ev);
+    for(auto ev : e->chunk_k)
+        if(ev)
+            cudaEventDestroy(ev);
+    if(e->ev_fork)
+        cudaEventDestroy(e->ev_fork);
+    if(e->ev_join)
+        cudaEventDestroy(e->ev_join);
+    if(e->s_h2d)
+        cudaStreamDestroy(e->s_h2d);
+    if(e->s_d2h)
+        cudaStreamDestroy(e->s_d2h);
     if(e->ev0)
         cudaEventDestroy(e->ev0);
     if(e->ev1)
@@ -543,110 +561,39 @@ int64_t wf_preview_table(const wf_config *cfg, int which, float *out, int64_t ca
     return copy_table(t, which, out, capacity);
 }
 
-int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
+// Launch the fused kernel for streams [s0, s0+count) of the batch; all pointers are DEVICE pointers already
+// offset to stream 0 of the batch.
+static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0, int count, const float *pcm,
+                        const float *rms, const unsigned char *skip, float *out_db, float *out_points,
+                        unsigned char *silent, float *out_peak)
 {
-    if(!e || !b)
-        return WF_ERR_INVALID_ARG;
-    if(b->struct_size != sizeof(wf_batch))
-        return set_err(e, WF_ERR_ABI, "wf_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_batch));
     const Tables &t = e->tab;
     const int cc = t.cfg.capture_channels, dch = t.display_channels, och = t.output_channels, B = t.B, N = t.N;
-    if(b->n_streams < 0 || b->n_frames < 0 || b->hop < 1)
-        return set_err(e, WF_ERR_INVALID_ARG, "n_streams/n_frames must be >= 0 and hop >= 1");
-    if(b->first_stream < 0 || (int64_t)b->first_stream + b->n_streams > t.cfg.max_streams)
-        return set_err(e, WF_ERR_CAPACITY, "streams [%d, %d) exceed max_streams %d", b->first_stream,
-                       b->first_stream + b->n_streams, t.cfg.max_streams);
-    if(b->n_streams == 0 || b->n_frames == 0)
-        return WF_OK;
-    if(!b->pcm)
-        return set_err(e, WF_ERR_INVALID_ARG, "pcm is null");
-    if(b->stream_stride < 0 || b->channel_stride < 0)
-        return set_err(e, WF_ERR_INVALID_ARG, "negative strides are not supported");
-    if(b->out_points && t.num_points <= 0)
-        return set_err(e, WF_ERR_INVALID_ARG, "out_points requested but the engine has no display points");
-
-    WF_CUDA(e, cudaSetDevice(e->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-    const bool dev_ptrs = is_device_ptr(b->pcm);
-    const size_t S = (size_t)b->n_streams, T = (size_t)b->n_frames;
-
+    const size_t T = (size_t)b->n_frames;
     KParams kp{};
-    const float *pcm = b->pcm;
-    float *out_db = b->out_db, *out_points = b->out_points, *out_peak = b->out_peak;
-    const float *rms = b->input_rms;
-    const unsigned char *skip = b->skip_mask;
-    unsigned char *silent = b->out_silent;
-    const size_t span = (S - 1) * (size_t)b->stream_stride + (size_t)(cc - 1) * (size_t)b->channel_stride +
-                        (T - 1) * (size_t)b->hop + (size_t)N;
-    if(!dev_ptrs)
-    {
-        int rc;
-        if((rc = ensure(e, &e->s_pcm, &e->s_pcm_cap, span)))
-            return rc;
-        WF_CUDA(e, cudaMemcpyAsync(e->s_pcm, b->pcm, span * sizeof(float), cudaMemcpyHostToDevice, st));
-        pcm = e->s_pcm;
-        if(b->out_db)
-        {
-            if((rc = ensure(e, &e->s_out_db, &e->s_out_db_cap, S * T * dch * B)))
-                return rc;
-            out_db = e->s_out_db;
-        }
-        if(b->out_points)
-        {
-            if((rc = ensure(e, &e->s_out_points, &e->s_out_points_cap, S * T * dch * t.num_points)))
-                return rc;
-            out_points = e->s_out_points;
-        }
-        if(b->input_rms)
-        {
-            if((rc = ensure(e, &e->s_rms, &e->s_rms_cap, S * T)))
-                return rc;
-            WF_CUDA(e, cudaMemcpyAsync(e->s_rms, b->input_rms, S * T * sizeof(float), cudaMemcpyHostToDevice, st));
-            rms = e->s_rms;
-        }
-        if(b->skip_mask)
-        {
-            if((rc = ensure(e, &e->s_skip, &e->s_skip_cap, S * T)))
-                return rc;
-            WF_CUDA(e, cudaMemcpyAsync(e->s_skip, b->skip_mask, S * T, cudaMemcpyHostToDevice, st));
-            skip = e->s_skip;
-        }
-        if(b->out_silent)
-        {
-            if((rc = ensure(e, &e->s_silent, &e->s_silent_cap, S * T)))
-                return rc;
-            silent = e->s_silent;
-        }
-        if(b->out_peak)
-        {
-            if((rc = ensure(e, &e->s_peak, &e->s_peak_cap, T)))
-                return rc;
-            out_peak = e->s_peak;
-        }
-    }
-
-    kp.pcm = pcm;
+    kp.pcm = pcm + (size_t)s0 * (size_t)b->stream_stride;
     kp.stream_stride = b->stream_stride;
     kp.channel_stride = b->channel_stride;
-    kp.n_streams = b->n_streams;
+    kp.n_streams = count;
     kp.n_frames = b->n_frames;
     kp.hop = b->hop;
-    kp.aligned8 = (((uintptr_t)pcm & 7u) == 0) && ((b->stream_stride & 1) == 0) && ((b->channel_stride & 1) == 0) &&
+    kp.aligned8 = (((uintptr_t)kp.pcm & 7u) == 0) && ((b->stream_stride & 1) == 0) && ((b->channel_stride & 1) == 0) &&
                   ((b->hop & 1) == 0);
-    kp.input_rms = rms;
-    kp.skip_mask = skip;
+    kp.input_rms = rms ? rms + (size_t)s0 * T : nullptr;
+    kp.skip_mask = skip ? skip + (size_t)s0 * T : nullptr;
     kp.window = e->d_window;
     kp.window2 = reinterpret_cast<const float2 *>(e->d_window);
     kp.tw = reinterpret_cast<const float2 *>(e->d_tw);
     kp.tw_post = reinterpret_cast<const float2 *>(e->d_tw_post);
     kp.slope = e->d_slope;
     kp.rolloff = e->d_rolloff;
-    kp.state = e->d_state + (size_t)b->first_stream * cc * B;
-    kp.hold_db = e->d_hold + (size_t)b->first_stream * och * B;
-    kp.flags = e->d_flags + b->first_stream;
-    kp.out_db = out_db;
-    kp.out_points = out_points;
-    kp.out_silent = silent;
+    const size_t slot = (size_t)b->first_stream + (size_t)s0;
+    kp.state = e->d_state + slot * cc * B;
+    kp.hold_db = e->d_hold + slot * och * B;
+    kp.flags = e->d_flags + slot;
+    kp.out_db = out_db ? out_db + (size_t)s0 * T * dch * B : nullptr;
+    kp.out_points = out_points ? out_points + (size_t)s0 * T * dch * t.num_points : nullptr;
+    kp.out_silent = silent ? silent + (size_t)s0 * T : nullptr;
     kp.out_peak = out_peak;
     kp.coef_half = (2.0f / t.window_sum) * 0.5f; // mag_coefficient/2: the split pass leaves 2*X (src/source_generic.cpp:110)
     kp.g = (t.cfg.tsmoothing == WF_TSMOOTH_NONE) ? 0.0f : gravity_for(t.cfg, b->seconds);
@@ -678,16 +625,9 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
     kp.gauss_sum = t.gauss_sum;
     kp.filter = (t.cfg.filter_mode == WF_FILTER_GAUSS);
 
-    WF_CUDA(e, cudaEventRecord(e->ev0, st));
-    if(out_peak)
-    {
-        int rc = fill_device(e, out_peak, (long long)T, -INFINITY, st);
-        if(rc)
-            return rc;
-    }
     // shared memory for the gaussian intermediate: [groups][2][num_points] floats
     size_t extra = 0;
-    if(out_points && kp.filter)
+    if(kp.out_points && kp.filter)
     {
         int groups = 1;
         switch(N)
@@ -701,34 +641,169 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         }
         extra = (size_t)groups * 2 * (size_t)t.num_points * sizeof(float);
     }
-    const bool aligned16 = (((uintptr_t)pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
-    const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && out_db && !out_points && aligned16 &&
+    const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
+    const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && aligned16 &&
                          !e->force_generic;
-    int rc;
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
-        rc = dispatch_fast2048(e, kp, st, x);
+        return dispatch_fast2048(e, kp, st, x);
     }
-    else
-        rc = (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
-    if(rc)
+    return (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
+}
+
+int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
+{
+    if(!e || !b)
+        return WF_ERR_INVALID_ARG;
+    if(b->struct_size != sizeof(wf_batch))
+        return set_err(e, WF_ERR_ABI, "wf_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_batch));
+    const Tables &t = e->tab;
+    const int cc = t.cfg.capture_channels, dch = t.display_channels, B = t.B, N = t.N;
+    if(b->n_streams < 0 || b->n_frames < 0 || b->hop < 1)
+        return set_err(e, WF_ERR_INVALID_ARG, "n_streams/n_frames must be >= 0 and hop >= 1");
+    if(b->first_stream < 0 || (int64_t)b->first_stream + b->n_streams > t.cfg.max_streams)
+        return set_err(e, WF_ERR_CAPACITY, "streams [%d, %d) exceed max_streams %d", b->first_stream,
+                       b->first_stream + b->n_streams, t.cfg.max_streams);
+    if(b->n_streams == 0 || b->n_frames == 0)
+        return WF_OK;
+    if(!b->pcm)
+        return set_err(e, WF_ERR_INVALID_ARG, "pcm is null");
+    if(b->stream_stride < 0 || b->channel_stride < 0)
+        return set_err(e, WF_ERR_INVALID_ARG, "negative strides are not supported");
+    if(b->out_points && t.num_points <= 0)
+        return set_err(e, WF_ERR_INVALID_ARG, "out_points requested but the engine has no display points");
+
+    WF_CUDA(e, cudaSetDevice(e->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    const bool dev_ptrs = is_device_ptr(b->pcm);
+    const size_t S = (size_t)b->n_streams, T = (size_t)b->n_frames;
+
+    if(dev_ptrs)
+    {
+        WF_CUDA(e, cudaEventRecord(e->ev0, st));
+        if(b->out_peak)
+        {
+            int rc = fill_device(e, b->out_peak, (long long)T, -INFINITY, st);
+            if(rc)
+                return rc;
+        }
+        int rc = launch_range(e, b, st, 0, b->n_streams, b->pcm, b->input_rms, b->skip_mask, b->out_db, b->out_points,
+                              b->out_silent, b->out_peak);
+        if(rc)
+            return rc;
+        WF_CUDA(e, cudaEventRecord(e->ev1, st));
+        e->ev_valid = true;
+        return WF_OK;
+    }
+
+    // ---- host buffers: stage through device memory, chunked over streams so that the H2D copy of chunk i+1, the
+    //      kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is full duplex; pinned memory required for
+    //      real overlap, pageable memory still works but serialises) ----
+    const size_t per_stream_span = (size_t)(cc - 1) * (size_t)b->channel_stride + (T - 1) * (size_t)b->hop + (size_t)N;
+    const size_t span = (S - 1) * (size_t)b->stream_stride + per_stream_span;
+    int rc;
+    if((rc = ensure(e, &e->s_pcm, &e->s_pcm_cap, span)))
         return rc;
+    float *d_out_db = nullptr, *d_out_points = nullptr, *d_rms = nullptr, *d_peak = nullptr;
+    unsigned char *d_skip = nullptr, *d_silent = nullptr;
+    if(b->out_db)
+    {
+        if((rc = ensure(e, &e->s_out_db, &e->s_out_db_cap, S * T * dch * B)))
+            return rc;
+        d_out_db = e->s_out_db;
+    }
+    if(b->out_points)
+    {
+        if((rc = ensure(e, &e->s_out_points, &e->s_out_points_cap, S * T * dch * t.num_points)))
+            return rc;
+        d_out_points = e->s_out_points;
+    }
+    if(b->input_rms)
+    {
+        if((rc = ensure(e, &e->s_rms, &e->s_rms_cap, S * T)))
+            return rc;
+        d_rms = e->s_rms;
+    }
+    if(b->skip_mask)
+    {
+        if((rc = ensure(e, &e->s_skip, &e->s_skip_cap, S * T)))
+            return rc;
+        d_skip = e->s_skip;
+    }
+    if(b->out_silent)
+    {
+        if((rc = ensure(e, &e->s_silent, &e->s_silent_cap, S * T)))
+            return rc;
+        d_silent = e->s_silent;
+    }
+    if(b->out_peak)
+    {
+        if((rc = ensure(e, &e->s_peak, &e->s_peak_cap, T)))
+            return rc;
+        d_peak = e->s_peak;
+    }
+    if(!e->s_h2d)
+    {
+        WF_CUDA(e, cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        WF_CUDA(e, cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+        for(auto &ev : e->chunk_in)
+            WF_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for(auto &ev : e->chunk_k)
+            WF_CUDA(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        WF_CUDA(e, cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        WF_CUDA(e, cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    }
+    const size_t in_bytes = span * sizeof(float);
+    int nchunks = (int)std::min<size_t>(std::min<size_t>(wf_engine::kMaxChunks, S), std::max<size_t>(1, in_bytes >> 25));
+    const int per = (int)((S + nchunks - 1) / nchunks);
+    nchunks = (int)((S + per - 1) / per);
+
+    WF_CUDA(e, cudaEventRecord(e->ev0, st));
+    WF_CUDA(e, cudaEventRecord(e->ev_fork, st));
+    WF_CUDA(e, cudaStreamWaitEvent(e->s_h2d, e->ev_fork, 0));
+    WF_CUDA(e, cudaStreamWaitEvent(e->s_d2h, e->ev_fork, 0));
+    if(d_peak)
+    {
+        if((rc = fill_device(e, d_peak, (long long)T, -INFINITY, st)))
+            return rc;
+    }
+    for(int c = 0; c < nchunks; ++c)
+    {
+        const int s0 = c * per;
+        const int cnt = std::min<int>(per, (int)S - s0);
+        const size_t off = (size_t)s0 * (size_t)b->stream_stride;
+        const size_t cspan = (size_t)(cnt - 1) * (size_t)b->stream_stride + per_stream_span;
+        WF_CUDA(e, cudaMemcpyAsync(e->s_pcm + off, b->pcm + off, cspan * sizeof(float), cudaMemcpyHostToDevice, e->s_h2d));
+        if(d_rms)
+            WF_CUDA(e, cudaMemcpyAsync(d_rms + (size_t)s0 * T, b->input_rms + (size_t)s0 * T, (size_t)cnt * T * sizeof(float),
+                                       cudaMemcpyHostToDevice, e->s_h2d));
+        if(d_skip)
+            WF_CUDA(e, cudaMemcpyAsync(d_skip + (size_t)s0 * T, b->skip_mask + (size_t)s0 * T, (size_t)cnt * T,
+                                       cudaMemcpyHostToDevice, e->s_h2d));
+        WF_CUDA(e, cudaEventRecord(e->chunk_in[c], e->s_h2d));
+        WF_CUDA(e, cudaStreamWaitEvent(st, e->chunk_in[c], 0));
+        if((rc = launch_range(e, b, st, s0, cnt, e->s_pcm, d_rms, d_skip, d_out_db, d_out_points, d_silent, d_peak)))
+            return rc;
+        WF_CUDA(e, cudaEventRecord(e->chunk_k[c], st));
+        WF_CUDA(e, cudaStreamWaitEvent(e->s_d2h, e->chunk_k[c], 0));
+        if(b->out_db)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_db + (size_t)s0 * T * dch * B, d_out_db + (size_t)s0 * T * dch * B,
+                                       (size_t)cnt * T * dch * B * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        if(b->out_points)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_points + (size_t)s0 * T * dch * t.num_points,
+                                       d_out_points + (size_t)s0 * T * dch * t.num_points,
+                                       (size_t)cnt * T * dch * t.num_points * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        if(b->out_silent)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_silent + (size_t)s0 * T, d_silent + (size_t)s0 * T, (size_t)cnt * T,
+                                       cudaMemcpyDeviceToHost, e->s_d2h));
+    }
     WF_CUDA(e, cudaEventRecord(e->ev1, st));
     e->ev_valid = true;
-
-    if(!dev_ptrs)
-    {
-        if(b->out_db)
-            WF_CUDA(e, cudaMemcpyAsync(b->out_db, out_db, S * T * dch * B * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if(b->out_points)
-            WF_CUDA(e, cudaMemcpyAsync(b->out_points, out_points, S * T * dch * t.num_points * sizeof(float),
-                                       cudaMemcpyDeviceToHost, st));
-        if(b->out_silent)
-            WF_CUDA(e, cudaMemcpyAsync(b->out_silent, silent, S * T, cudaMemcpyDeviceToHost, st));
-        if(b->out_peak)
-            WF_CUDA(e, cudaMemcpyAsync(b->out_peak, out_peak, T * sizeof(float), cudaMemcpyDeviceToHost, st));
-    }
+    if(b->out_peak) // complete only after the last chunk's kernel
+        WF_CUDA(e, cudaMemcpyAsync(b->out_peak, d_peak, T * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+    WF_CUDA(e, cudaEventRecord(e->ev_join, e->s_d2h));
+    WF_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0)); // the caller's stream completes when the results are home
     return WF_OK;
 }
 
