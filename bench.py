@@ -5,7 +5,7 @@
   python bench.py --impl reference --gpus N ...          # the reference's own CPU path (oracle/_ref), all host cores
 
 One "step" = one pass of the hot path over one batch of synthetic 48 kHz PCM already resident in HBM:
-65 536 mono frames of N=2048 per GPU, laid out as 4096 independent streams x 16 consecutive frames (hop = N)
+65 536 mono frames of N=2048 per GPU, laid out as 2048 independent streams x 32 consecutive frames (hop = N)
 so that the EMA recurrence state stays on-chip between frames.  Inputs (512 MiB)
 and outputs (256 MiB) are each larger than the 126 MB L2, so every step streams from/to HBM.
 
@@ -139,7 +139,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", gpu_id], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                          "-lms", "20", "-i", gpu_id], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                                          text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -150,13 +150,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
     def stop(self, t_begin, t_end):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        rows = [r for (t, r) in self.rows if t_begin - 0.06 <= t <= t_end + 0.06] or [r for (_, r) in self.rows]
+        # nvidia-smi stamps a sample up to one period after the state it shows; take the samples around the timed region
+        rows = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05] or \
+               [r for (t, r) in self.rows if t_begin - 0.1 <= t <= t_end + 0.15] or [r for (_, r) in self.rows]
         for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
@@ -174,7 +181,7 @@ class ClockSampler:
 
 
 def workload_name():
-    return ("c3: 65536 mono frames/GPU, N=2048 Hann, EMA g=0.65, dBFS; 4096 streams x 16 consecutive frames, hop=N "
+    return ("c3: 65536 mono frames/GPU, N=2048 Hann, EMA g=0.65, dBFS; 2048 streams x 32 consecutive frames, hop=N "
             "(BASELINE.json configs[2])")
 
 
@@ -234,13 +241,14 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
-
     props = torch.cuda.get_device_properties(device)
     gpu_id = "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank)
     sampler = ClockSampler(gpu_id) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     launches0 = eng.launch_count
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_begin = time.perf_counter()
@@ -324,11 +332,11 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4096, help="independent streams per GPU")
-    ap.add_argument("--frames", type=int, default=16, help="consecutive frames per stream")
+    ap.add_argument("--streams", type=int, default=2048, help="independent streams per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="consecutive frames per stream")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-frames-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                 v[pidx] = pk::mul(v[pidx], win64[lane + 32 * pidx]);
             const bool nz = __any_sync(0xffffffffu, (nzbits & 0x7fffffff7fffffffull) != 0ull);
 
-            // ---- two radix-32 register passes sharing one copy of the butterfly code ----
-#pragma unroll 1
+            // ---- two radix-32 register passes (unrolled: a rolled loop costs ~70 register moves per frame at the
+            //      back-edge, and the code still fits the instruction cache) ----
+#pragma unroll
             for(int pass = 0; pass < 2; ++pass)
             {
                 pk::dft_bitrev<32>(v);
