@@ -5,7 +5,7 @@
   python bench.py --impl reference --gpus N ...          # the reference's own CPU path (oracle/_ref), all host cores
 
 One "step" = one pass of the hot path over one batch of synthetic 48 kHz PCM already resident in HBM:
-65 536 mono frames of N=2048 per GPU, laid out as 2048 independent streams x 32 consecutive frames (hop = N)
+65 536 mono frames of N=2048 per GPU, laid out as 4096 independent streams x 16 consecutive frames (hop = N)
 so that the EMA recurrence state stays on-chip between frames.  Inputs (512 MiB)
 and outputs (256 MiB) are each larger than the 126 MB L2, so every step streams from/to HBM.
 
@@ -181,7 +181,7 @@ class ClockSampler:
 
 
 def workload_name():
-    return ("c3: 65536 mono frames/GPU, N=2048 Hann, EMA g=0.65, dBFS; 2048 streams x 32 consecutive frames, hop=N "
+    return ("c3: 65536 mono frames/GPU, N=2048 Hann, EMA g=0.65, dBFS; 4096 streams x 16 consecutive frames, hop=N "
             "(BASELINE.json configs[2])")
 
 
@@ -335,8 +335,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=2048, help="independent streams per GPU")
-    ap.add_argument("--frames", type=int, default=32, help="consecutive frames per stream")
+    ap.add_argument("--streams", type=int, default=4096, help="independent streams per GPU")
+    ap.add_argument("--frames", type=int, default=16, help="consecutive frames per stream")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-frames-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")

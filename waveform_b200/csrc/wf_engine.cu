@@ -35,6 +35,7 @@ struct wf_engine {
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
+    bool use_pdl = true;        // WF_NO_PDL=1: launch the fast kernel without programmatic dependent launch
 
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
@@ -166,24 +167,13 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     }
 }
 
-// Pick warps/SM so that whole streams (the unit of work: EMA state stays on-chip across a stream's frames)
-// spread evenly over the SMs:  rounds * warps_per_sm * sm_count >= n_streams with the least waste.
+// One CTA per SM; the kernel deals streams round-robin to CTAs first, so each SM gets n_streams/grid (+-1) whole
+// streams (the unit of work: EMA state stays on-chip across a stream's frames) and runs min(max_wpc, that) warps.
 static void fast2048_geometry(int n_streams, int sm_count, int max_wpc, int *warps_per_cta, int *grid)
 {
-    int best_w = max_wpc, best_cost = 1 << 30;
-    for(int w = max_wpc; w >= 8; --w) // one CTA per SM with w warps
-    {
-        const int rounds = (n_streams + sm_count * w - 1) / (sm_count * w);
-        const int cost = rounds * w; // time ~ rounds * (per-SM issue load ~ w warps sharing the SM)
-        if(cost < best_cost)
-        {
-            best_cost = cost;
-            best_w = w;
-        }
-    }
-    *warps_per_cta = best_w;
-    const int ctas_needed = (n_streams + best_w - 1) / best_w;
-    *grid = std::min(ctas_needed, sm_count);
+    *grid = std::min(n_streams, sm_count);
+    const int per_cta = (n_streams + *grid - 1) / *grid;
+    *warps_per_cta = std::max(1, std::min(max_wpc, per_cta));
 }
 
 template<int MAXW, bool TSM, bool GATE, bool EXTRA>
@@ -202,10 +192,19 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
     if(e->fast_wpc_override > 0 && e->fast_wpc_override <= MAXW)
     {
         wpc = e->fast_wpc_override;
-        grid = std::min((kp.n_streams + wpc - 1) / wpc, e->sm_count);
+        grid = std::min(kp.n_streams, e->sm_count);
     }
-    stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA><<<grid, wpc * 32, fast::smem_bytes(wpc), st>>>(kp);
-    WF_CUDA(e, cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(wpc * 32));
+    cfg.dynamicSmemBytes = fast::smem_bytes(wpc);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // PDL: prologue overlaps the previous launch's tail
+    attr[0].val.programmaticStreamSerializationAllowed = e->use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WF_CUDA(e, cudaLaunchKernelEx(&cfg, stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA>, kp));
     e->launches++;
     return WF_OK;
 }
@@ -387,6 +386,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *mw = getenv("WF_FAST_MAXW");
         if(mw && (atoi(mw) == 12 || atoi(mw) == 16))
             e->fast_maxw = atoi(mw);
+        const char *np = getenv("WF_NO_PDL");
+        e->use_pdl = !(np && np[0] == '1');
         const char *wo = getenv("WF_FAST_WPC");
         if(wo)
             e->fast_wpc_override = atoi(wo);

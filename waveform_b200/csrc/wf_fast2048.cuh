@@ -131,10 +131,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: everything above (tables, barriers) touches only immutable data and may overlap
+    // the tail of the previous launch on this stream; per-stream state / PCM / outputs are touched only after the
+    // previous grid has completed and flushed.  Let the next launch start its own prologue as early as possible.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    const int total_warps = gridDim.x * warps_per_cta;
-    const int gw = blockIdx.x * warps_per_cta + warp;
+    // Streams are dealt round-robin to CTAs (= SMs) first and to the CTA's warps second, so every SM gets
+    // n_streams/gridDim (+-1) streams whatever the warp count: stream of (cta c, local index i) = c + i*gridDim.
     const int S = p.n_streams, T = p.n_frames;
+    const int G = gridDim.x;
+    const int n_local = (S > (int)blockIdx.x) ? (S - (int)blockIdx.x + G - 1) / G : 0;
     constexpr int B = kM;
     uint32_t phase = 0;
 
@@ -143,14 +150,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
     const int kb = jp + (lane == 0 ? 32 : 0);
     const int k2_q0 = (lane == 0) ? 512 : (kb + 992);
 
-    if(gw < S && lane == 0)
+    if(warp < n_local && lane == 0)
     {
         mbar_expect_tx(mbar, kN * 4);
-        tma_load_1d(buf, p.pcm + (size_t)gw * p.stream_stride, kN * 4, mbar);
+        tma_load_1d(buf, p.pcm + (size_t)(blockIdx.x + warp * G) * p.stream_stride, kN * 4, mbar);
     }
 
-    for(int s = gw; s < S; s += total_warps)
+    for(int li = warp; li < n_local; li += warps_per_cta)
     {
+        const int s = (int)blockIdx.x + li * G;
         // ---- per-stream state: global (natural bin order) -> shared ([pair][lane]) ----
         {
             const float *sp = p.state + (size_t)s * B;
@@ -215,8 +223,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                         const float *next = nullptr;
                         if(t + 1 < T)
                             next = pcm_s + (size_t)(t + 1) * p.hop;
-                        else if(s + total_warps < S)
-                            next = p.pcm + (size_t)(s + total_warps) * p.stream_stride;
+                        else if(li + warps_per_cta < n_local)
+                            next = p.pcm + (size_t)(s + warps_per_cta * G) * p.stream_stride;
                         if(next != nullptr)
                         {
                             fence_proxy_async();
