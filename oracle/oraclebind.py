@@ -231,6 +231,20 @@ class OracleSource:
         self.L.wfo_interp(self.h, ch, _fp(out))
         return out
 
+    def interp_of(self, db):
+        """Display points the reference's interpolation (+ Gaussian) yields for GIVEN dB spectra db[..., dch, B]
+        (loads them into m_decibels, then src/filter.hpp:133-211 as restated in wfo_interp)."""
+        db = np.ascontiguousarray(db, dtype=np.float32)
+        lead = db.shape[:-2]
+        flat = db.reshape(-1, db.shape[-2], db.shape[-1])
+        out = np.zeros((flat.shape[0], flat.shape[1], self.num_points), dtype=np.float32)
+        for i in range(flat.shape[0]):
+            for ch in range(flat.shape[1]):
+                row = np.ascontiguousarray(flat[i, ch])
+                self.L.wfo_set_state(self.h, ch, None, _fp(row))
+                self.L.wfo_interp(self.h, ch, _fp(out[i, ch]))
+        return out.reshape(*lead, flat.shape[1], self.num_points)
+
     def run_stft(self, pcm, n_frames, hop, seconds=1.0 / 60.0, rms=None, want_db=True, want_points=False):
         pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)
         ch0 = pcm[0]

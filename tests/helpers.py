@@ -57,3 +57,16 @@ def parity_report(got_db, ref_db, db_min=-758.0):
         "worst_excess": float((d / tol).max()),
         "same_floor": same_floor,
     }
+
+
+def check_points(settings, channels, got_db, got_points):
+    """Display points are a linear map of the dB spectrum (interpolation + Gaussian, src/filter.hpp:133-211): check the
+    CUDA epilogue against the oracle's interpolation applied to the CUDA path's OWN dB spectrum, so that this test
+    isolates the interpolation arithmetic (the spectrum itself is judged by parity_report)."""
+    from oracle.oraclebind import OracleSource
+
+    o = OracleSource(settings, channels=channels)
+    exp = o.interp_of(got_db)
+    d = np.abs(np.asarray(got_points, dtype=np.float64) - exp.astype(np.float64))
+    scale = np.maximum(np.abs(exp).max(axis=-1, keepdims=True), 1.0)
+    return float((d / scale).max())

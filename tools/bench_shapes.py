@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the BASELINE.json configs other than the headline (generic kernel path).
+Prints frames/s and the fraction of the measured HBM roofline using SURVEY §8(d) nominal bytes
+(hop*4 per channel in + written floats out per frame)."""
+import json, sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import torch
+from waveform_b200 import Engine
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+SHAPES = [
+    ("c2 stereo N=4096 BH, hop 800 (60 fps)", {"fft_size": 4096, "window": "blackman_harris", "channel_mode": "stereo"}, 2, 2048, 16, 800, "db"),
+    ("c4 N=8192 hop 2048, 800-pt Lanczos curve", {"fft_size": 8192, "window": "hann", "interp_mode": "lanczos"}, 1, 256, 256, 2048, "points"),
+    ("c4' N=8192 hop 2048, bins out", {"fft_size": 8192, "window": "hann"}, 1, 256, 256, 2048, "db"),
+    ("c5 N=16384 hop N, peak", {"fft_size": 16384, "window": "hann"}, 1, 128, 64, 16384, "db+peak"),
+    ("c1 N=1024 bars catrom", {"fft_size": 1024, "window": "hann", "display_mode": "bars", "interp_mode": "catmull_rom"}, 1, 4096, 16, 1024, "points"),
+    ("N=2048 generic (WF_FORCE_GENERIC)", {"fft_size": 2048, "window": "hann"}, 1, 4096, 16, 2048, "db"),
+]
+for name, settings, ch, S, T, hop, mode in SHAPES:
+    import os
+    if "FORCE_GENERIC" in name:
+        os.environ["WF_FORCE_GENERIC"] = "1"
+    eng = Engine(settings, channels=ch, max_streams=S)
+    os.environ.pop("WF_FORCE_GENERIC", None)
+    N, cc, dch, B, P = eng.fft_size, eng.capture_channels, eng.display_channels, eng.bins, eng.num_points
+    ns = (T - 1) * hop + N
+    pcm = (torch.rand((S, cc, ns), device="cuda") - 0.5) * 0.5
+    out_db = torch.empty((S, T, dch, B), device="cuda") if "db" in mode else None
+    out_pts = torch.empty((S, T, dch, P), device="cuda") if "points" in mode else None
+    peak = torch.empty((T,), device="cuda") if "peak" in mode else None
+    st = torch.cuda.Stream()
+    def step():
+        eng.process_raw(pcm.data_ptr(), S, T, hop, cc * ns, ns, out_db=None if out_db is None else out_db.data_ptr(),
+                        out_points=None if out_pts is None else out_pts.data_ptr(),
+                        out_peak=None if peak is None else peak.data_ptr(), stream=st.cuda_stream, sync=False)
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    K = 10
+    e0.record(st)
+    for _ in range(K): step()
+    e1.record(st); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    frames = S * T
+    out_floats = (dch * B if out_db is not None else 0) + (dch * P if out_pts is not None else 0)
+    bytes_per_frame = min(hop, N) * 4 * cc + out_floats * 4
+    gbs = frames * bytes_per_frame / (ms * 1e-3) / 1e9
+    print(f"{name:45s} {frames/ms/1e3:9.2f} M frames/s  {ms*1e3:9.1f} us/launch  {bytes_per_frame:6d} B/frame  {gbs:7.1f} GB/s  frac {gbs/PEAK:.3f}")

@@ -18,6 +18,7 @@
 
 #include "wf_kernels.cuh"
 #include "wf_fast2048.cuh"
+#include "wf_anyn.cuh"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -108,13 +109,56 @@ int ensure(wf_engine *e, T **buf, size_t *cap, size_t need)
     return WF_OK;
 }
 
-bool supported_fft_size(int n)
+bool is_pow2_kernel_size(int n)
 {
     switch(n)
     {
     case 128: case 256: case 512: case 1024: case 2048: case 4096: case 8192: case 16384: case 32768: return true;
     default: return false;
     }
+}
+
+// Run-time plan of the any-N kernel: factors of M = N/2, twos grouped up to 16, odd primes as they are.
+bool make_any_plan(int n, AnyPlan *plan)
+{
+    if(n < 128 || (n & 15))
+        return false;
+    int m = n / 2;
+    plan->M = m;
+    plan->n_pass = 0;
+    int twos = 0;
+    while((m & 1) == 0)
+    {
+        m >>= 1;
+        ++twos;
+    }
+    while(twos > 0)
+    {
+        const int g = (twos >= 4) ? 4 : twos;
+        plan->radix[plan->n_pass++] = 1 << g;
+        twos -= g;
+    }
+    for(int f = 3; m > 1; f += 2)
+        while(m % f == 0)
+        {
+            if(plan->n_pass >= 20)
+                return false;
+            plan->radix[plan->n_pass++] = f;
+            m /= f;
+        }
+    return true;
+}
+
+// Power-of-two sizes 128..32768 take the templated kernels; other multiples of 16 take the any-N kernel as long as
+// two N/2-point complex buffers fit in shared memory.
+bool supported_fft_size(int n)
+{
+    if(is_pow2_kernel_size(n))
+        return true;
+    AnyPlan pl;
+    if(!make_any_plan(n, &pl))
+        return false;
+    return (size_t)pl.M * 16 + 8192 <= 220 * 1024 && (n & (n - 1)) != 0;
 }
 
 bool is_device_ptr(const void *p)
@@ -163,8 +207,24 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     case 8192: return launch_fused<8192, CC>(e, kp, st, extra);
     case 16384: return launch_fused<16384, CC>(e, kp, st, extra);
     case 32768: return launch_fused<32768, CC>(e, kp, st, extra);
-    default: return set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d has no kernel", e->tab.N);
+    default: break;
     }
+    // any other multiple of 16: run-time mixed-radix kernel
+    AnyPlan plan;
+    if(!make_any_plan(e->tab.N, &plan))
+        return set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d has no kernel", e->tab.N);
+    const size_t smem = (size_t)plan.M * 16 + extra;
+    static thread_local size_t configured[8] = {0};
+    const int dev = e->device & 7;
+    if(smem > 48 * 1024 && configured[dev] < smem)
+    {
+        WF_CUDA(e, cudaFuncSetAttribute(stft_anyn_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    stft_anyn_kernel<CC><<<kp.n_streams, kAnyThreads, smem, st>>>(kp, plan);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return WF_OK;
 }
 
 // One CTA per SM; the kernel deals streams round-robin to CTAs first, so each SM gets n_streams/grid (+-1) whole
@@ -289,7 +349,7 @@ const char *wf_strerror(int status)
     {
     case WF_OK: return "ok";
     case WF_ERR_INVALID_ARG: return "invalid argument";
-    case WF_ERR_UNSUPPORTED_FFT_SIZE: return "unsupported fft_size (supported: powers of two 128..32768)";
+    case WF_ERR_UNSUPPORTED_FFT_SIZE: return "unsupported fft_size (supported: multiples of 16 from 128; powers of two up to 32768, others up to ~27000)";
     case WF_ERR_CUDA: return "CUDA error";
     case WF_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU fallback)";
     case WF_ERR_OOM: return "out of device memory";
