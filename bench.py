@@ -35,6 +35,17 @@ BINS = N_FFT // 2
 BYTES_PER_FRAME = N_FFT * 4 + BINS * 4  # PCM in + bins out
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None if there is no capture."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        return float(d["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -295,6 +306,7 @@ def run_gpu_arm(args):
 
     if rank == 0:
         peak_gbs, peak_src = load_peaks()
+        traffic, traffic_src = load_traffic() if (S, T) == (4096, 16) else (None, None)
         kernel_ms = statistics.mean(per_launch)
         achieved = frames_per_gpu * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
         cpu = None
@@ -317,7 +329,8 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": int(h_out.numel() * 4), "steps": e2e_steps, "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": "stft2048_fast_kernel<16,true,true,false> (csrc/wf_fast2048.cuh)", "kernel_ms": kernel_ms,
                          "bytes_per_launch": frames_per_gpu * BYTES_PER_FRAME},
             "cpu_baseline": cpu,

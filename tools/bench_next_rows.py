@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Measurements for the SURVEY §8(f) 'next' rows already built:
+  rank 1  non-power-of-two N (any-N kernel): device-resident throughput + fraction of the measured HBM roofline
+  rank 2  live adapter: per-tick latency of wf_process (1 source, 1 tick, host buffers) next to the reference's
+          own tick_spectrum on one host core (oracle/_ref)."""
+import json, sys, time
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import torch
+from waveform_b200 import Engine
+from helpers import synth_pcm
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+print("== rank 1: non-power-of-two sizes, device-resident, S=4096 streams x T=16 ticks, hop=N")
+for N in (800, 1920, 2000, 4160):
+    S, T = 4096, 16
+    eng = Engine({"fft_size": N, "window": "hann"}, channels=1, max_streams=S)
+    pcm = (torch.rand((S, 1, T * N), device="cuda") - 0.5) * 0.5
+    out = torch.empty((S, T, 1, N // 2), device="cuda")
+    st = torch.cuda.Stream()
+    step = lambda: eng.process_raw(pcm.data_ptr(), S, T, N, T * N, T * N, out_db=out.data_ptr(), stream=st.cuda_stream, sync=False)
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(10): step()
+    e1.record(st); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    b = S * T * (N * 4 + N // 2 * 4)
+    print(f"  N={N:5d}: {S*T/ms/1e3:8.2f} M frames/s  {ms*1e3:8.1f} us/launch  {b/ms/1e6:7.1f} GB/s  frac_of_measured_hbm {b/ms/1e6/PEAK:.3f}")
+
+print("== rank 2: live tick latency (1 stereo source, N=4096, host buffers, wf_process blocking)")
+N = 4096
+eng = Engine({"fft_size": N, "channel_mode": "stereo"}, channels=2, max_streams=1)
+x = synth_pcm(1, 2, N)
+lat = []
+for i in range(300):
+    t0 = time.perf_counter(); eng.process(x, 1, N); lat.append(time.perf_counter() - t0)
+lat = np.array(lat[50:]) * 1e6
+print(f"  wf_process per tick: median {np.median(lat):.1f} us  p95 {np.percentile(lat,95):.1f} us  (includes ctypes + 2 pageable copies + launch)")
+try:
+    from oracle import refbind
+    for impl, name in ((refbind.IMPL_GENERIC, "generic"), (refbind.IMPL_AVX2, "AVX2")):
+        r = refbind.RefSource({"fft_size": N, "channel_mode": "stereo"}, impl=impl, channels=2)
+        pcm = synth_pcm(1, 2, 801 * 800 + N)[0]
+        t0 = time.perf_counter(); r.run_stft(pcm, 800, 800, want_db=False); dt = time.perf_counter() - t0
+        print(f"  reference WAVSource{name}::tick (capture+tick, 1 core): {dt/800*1e6:.1f} us per tick")
+except Exception as ex:
+    print("  reference unavailable:", ex)

@@ -7,7 +7,7 @@ timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | 
 timeout 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/bench_reference.json 2>gpurun_out/bench_reference.err
 timeout 300 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_ours.json 2>gpurun_out/bench_ours.err
 tail -c 1500 gpurun_out/bench_ours.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"stft|fill_kernel|peak_normalize" -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launches.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft2048 -s 4 -c 1 -o gpurun_out/prof_final \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-frames = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+frames = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 65536
 WANT = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -39,6 +39,11 @@ for r in rows[2:]:
         mulw = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index("dram__bytes_write.sum")]]
         print(f"  -> duration {t_s*1e3:.4f} ms (under ncu, cold), dram traffic {(rd*mul+wr*mulw)/1e6:.1f} MB, "
               f"{frames/t_s/1e6:.1f} M frames/s")
+        if "--traffic" in sys.argv:
+            import json, os
+            out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json")
+            json.dump({"kernel": r[hdr.index("Kernel Name")], "dram_bytes_per_launch": rd * mul + wr * mulw,
+                       "dram_read": rd * mul, "dram_write": wr * mulw, "source": os.path.basename(rep)}, open(out, "w"))
     except Exception as ex:
         print("  (derived failed)", ex)
 
