@@ -6,8 +6,9 @@ try:
     print(f\"  value {d['value']/1e6:8.1f} M/s  kernel {r['kernel_ms']*1e3:7.1f} us  frac {r['frac']:.3f}  clocks {d['clocks']['sm_mhz']}\")
 except Exception as ex:
     print('  FAILED/timeout', ex)"; }
-echo "S=2048xT=32"; run
-echo "S=4096xT=16"; run --streams 4096 --frames 16
-echo "S=4096xT=16 wpc=14"; WF_FAST_WPC=14 run --streams 4096 --frames 16
-echo "S=8192xT=8"; run --streams 8192 --frames 8
-echo "S=65536xT=1"; run --streams 65536 --frames 1
+echo "A S=4096xT=16"; WF_FAST_KERNEL=a run
+echo "B S=4096xT=16"; WF_FAST_KERNEL=b run
+echo "B S=4096xT=16 groups=12"; WF_FAST_KERNEL=b WF_FAST_WPC=12 run
+echo "B S=2048xT=32"; WF_FAST_KERNEL=b run --streams 2048 --frames 32
+echo "B S=8192xT=8"; WF_FAST_KERNEL=b run --streams 8192 --frames 8
+echo "B S=65536xT=1"; WF_FAST_KERNEL=b run --streams 65536 --frames 1

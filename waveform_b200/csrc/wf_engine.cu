@@ -19,6 +19,9 @@
 #include "wf_kernels.cuh"
 #include "wf_fast2048.cuh"
 #include "wf_anyn.cuh"
+#ifdef WF_BUILD_EXPERIMENTAL
+#include "experimental/wf_fast2048b.cuh"
+#endif
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -37,6 +40,7 @@ struct wf_engine {
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
     bool use_pdl = true;        // WF_NO_PDL=1: launch the fast kernel without programmatic dependent launch
+    char fast_kernel = 'a';     // WF_FAST_KERNEL=b selects csrc/experimental/wf_fast2048b.cuh when built with -DWF_BUILD_EXPERIMENTAL
 
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
@@ -269,9 +273,56 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
     return WF_OK;
 }
 
+#ifdef WF_BUILD_EXPERIMENTAL
+template<bool TSM, bool GATE, bool EXTRA>
+int launch_pair2048(wf_engine *e, const KParams &kp, cudaStream_t st)
+{
+    static thread_local bool configured[8] = {false};
+    const int dev = e->device & 7;
+    if(!configured[dev])
+    {
+        WF_CUDA(e, cudaFuncSetAttribute(stft2048_pair_kernel<TSM, GATE, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        fastb::smem_bytes(fastb::kMaxGroups)));
+        configured[dev] = true;
+    }
+    const int grid = std::min(kp.n_streams, e->sm_count);
+    const int per_cta = (kp.n_streams + grid - 1) / grid;
+    int groups = std::max(1, std::min(fastb::kMaxGroups, per_cta));
+    if(e->fast_wpc_override > 0 && e->fast_wpc_override <= fastb::kMaxGroups)
+        groups = e->fast_wpc_override;
+    stft2048_pair_kernel<TSM, GATE, EXTRA><<<grid, groups * 64, fastb::smem_bytes(groups), st>>>(kp);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    return WF_OK;
+}
+
+int dispatch_pair2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
+{
+    const bool tsm = kp.tsmooth != 0, gate = kp.gate != 0;
+#define WF_PAIR_CASE(T, G, X)                   \
+    if(tsm == T && gate == G && extra == X)     \
+        return launch_pair2048<T, G, X>(e, kp, st);
+    WF_PAIR_CASE(true, true, false)
+    WF_PAIR_CASE(true, true, true)
+    WF_PAIR_CASE(true, false, false)
+    WF_PAIR_CASE(true, false, true)
+    WF_PAIR_CASE(false, true, false)
+    WF_PAIR_CASE(false, true, true)
+    WF_PAIR_CASE(false, false, false)
+    WF_PAIR_CASE(false, false, true)
+#undef WF_PAIR_CASE
+    return set_err(e, WF_ERR_INVALID_ARG, "pair2048 dispatch fell through");
+}
+
+#endif
+
 // Hand-specialised path for the headline shape (see wf_fast2048.cuh); everything else takes the generic kernel.
 int dispatch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
 {
+#ifdef WF_BUILD_EXPERIMENTAL
+    if(e->fast_kernel == 'b')
+        return dispatch_pair2048(e, kp, st, extra);
+#endif
     const bool tsm = kp.tsmooth != 0, gate = kp.gate != 0;
     const int maxw = e->fast_maxw;
 #define WF_FAST_CASE(W, T, G, X)            \
@@ -446,6 +497,9 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *mw = getenv("WF_FAST_MAXW");
         if(mw && (atoi(mw) == 12 || atoi(mw) == 16))
             e->fast_maxw = atoi(mw);
+        const char *fk = getenv("WF_FAST_KERNEL");
+        if(fk && (fk[0] == 'a' || fk[0] == 'b'))
+            e->fast_kernel = fk[0];
         const char *np = getenv("WF_NO_PDL");
         e->use_pdl = !(np && np[0] == '1');
         const char *wo = getenv("WF_FAST_WPC");
