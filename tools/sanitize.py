@@ -1,0 +1,27 @@
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck) covering the three kernels.
+Run:  PYTORCH_NO_CUDA_MEMORY_CACHING=1 compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import numpy as np, torch
+from waveform_b200 import Engine
+from helpers import synth_pcm
+CASES = [({"fft_size": 2048}, 1, 20, 3, 1, False),
+         ({"fft_size": 2048, "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0, "normalize_volume": True}, 1, 5, 3, 1, False),
+         ({"fft_size": 1024, "channel_mode": "stereo", "interp_mode": "lanczos", "filter_mode": "gauss"}, 2, 3, 3, 2, True),
+         ({"fft_size": 4096, "display_mode": "bars"}, 2, 2, 3, 4, True),
+         ({"fft_size": 800}, 1, 3, 3, 1, True),
+         ({"fft_size": 256}, 1, 9, 3, 1, True),
+         ({"fft_size": 128, "channel_mode": "stereo"}, 2, 17, 2, 1, True),
+         ({"fft_size": 16384}, 1, 2, 2, 2, False)]
+for s, ch, S, T, hopdiv, pts in CASES:
+    e = Engine(s, channels=ch, max_streams=S); N = e.fft_size; hop = N // hopdiv
+    x = synth_pcm(S, e.capture_channels, (T - 1) * hop + N); x[0, :, :] = 0
+    rms = np.full((S, T), 0.1, np.float32) if s.get("normalize_volume") else None
+    o = e.process(torch.from_numpy(x).cuda(), T, hop, want_points=pts, want_peak=True,
+                  input_rms=None if rms is None else torch.from_numpy(rms))
+    torch.cuda.synchronize()
+    o2 = Engine(s, channels=ch, max_streams=S).process(x, T, hop, want_points=pts, input_rms=rms)  # host-pointer path
+    assert np.array_equal(o["db"].cpu().numpy(), o2["db"])
+    print(s.get("fft_size"), "ok", float(o["db"].float().mean()), flush=True)

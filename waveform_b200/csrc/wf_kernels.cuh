@@ -100,25 +100,32 @@ struct Geo {
 __device__ __forceinline__ int phys(int i) { return i + (i >> 5); }
 
 // ---- group-level sync / votes -----------------------------------------------------------------------
+// Sub-warp groups (TN < 32: several streams share a warp) may diverge from one another (one stream is gated
+// while its neighbour is not), so every warp-level primitive names only the lanes of the calling group.
+template<int TN>
+__device__ __forceinline__ unsigned group_mask()
+{
+    if constexpr(TN >= 32)
+        return 0xffffffffu;
+    else
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        return ((1u << TN) - 1u) << (lane & ~(unsigned)(TN - 1));
+    }
+}
 template<int TN>
 __device__ __forceinline__ void group_sync()
 {
     if constexpr(TN <= 32)
-        __syncwarp();
+        __syncwarp(group_mask<TN>());
     else
         __syncthreads();
 }
 template<int TN>
 __device__ __forceinline__ bool group_any(bool x)
 {
-    if constexpr(TN == 32)
-        return __any_sync(0xffffffffu, x);
-    else if constexpr(TN < 32)
-    {
-        const unsigned lane = threadIdx.x & 31u;
-        const unsigned mask = ((1u << TN) - 1u) << (lane & ~(unsigned)(TN - 1));
-        return (__ballot_sync(0xffffffffu, x) & mask) != 0u;
-    }
+    if constexpr(TN <= 32)
+        return __ballot_sync(group_mask<TN>(), x) != 0u;
     else
         return __syncthreads_or(x) != 0;
 }
@@ -132,9 +139,10 @@ __device__ __forceinline__ float group_max(float x, float *scratch)
 {
     if constexpr(TN <= 32)
     {
+        const unsigned m = group_mask<TN>();
 #pragma unroll
         for(int o = TN / 2; o > 0; o >>= 1)
-            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+            x = fmaxf(x, __shfl_xor_sync(m, x, o));
         return x;
     }
     else
