@@ -17,6 +17,8 @@ struct AnyPlan {
     int M;          // N/2
     int n_pass;
     int radix[20];
+    float2 *scratch; // per-CTA [2][M] complex work buffers in global memory (L2) when they do not fit in shared
+                     // memory (N > ~27000, e.g. the plugin's "large FFT" sizes up to 65536); null = shared memory
 };
 
 constexpr int kAnyThreads = 256;
@@ -27,15 +29,18 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int M = plan.M, B = plan.M;
-    float2 *bufA = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufA = (plan.scratch != nullptr) ? plan.scratch + (size_t)blockIdx.x * 2 * M : reinterpret_cast<float2 *>(smem_raw);
     float2 *bufB = bufA + M;
-    float *pts = reinterpret_cast<float *>(bufB + M); // [dch][n_points] (only when filtering display points)
+    // [dch][n_points] intermediate of the Gaussian (only when filtering display points)
+    float *pts = (plan.scratch != nullptr) ? reinterpret_cast<float *>(smem_raw) : reinterpret_cast<float *>(bufB + M);
     __shared__ float red_scratch[32];
     const int tid = threadIdx.x;
-    const int s = blockIdx.x;
     const int dch = p.dch, och = p.och;
     const bool stereo = p.stereo != 0;
     const int T = p.n_frames;
+
+    for(int s = blockIdx.x; s < p.n_streams; s += gridDim.x)
+    {
 
     float *state_s = p.state + (size_t)s * CC * B;
     float *hold_s = p.hold_db + (size_t)s * och * B;
@@ -273,6 +278,8 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
             hold_s[B + k] = state_s[B + k];
     if(tid == 0)
         p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent0 ? 2u : 0u) | (prev_out_silent1 ? 4u : 0u));
+    __syncthreads();
+    } // streams
 }
 
 } // namespace wf

@@ -53,6 +53,8 @@ struct wf_engine {
     // staging for host-pointer batches (grown on demand)
     float *s_pcm = nullptr, *s_out_db = nullptr, *s_out_points = nullptr, *s_rms = nullptr, *s_peak = nullptr;
     unsigned char *s_skip = nullptr, *s_silent = nullptr;
+    float *s_scratch = nullptr; // any-N kernel work buffers when N/2 complex points x 2 exceed shared memory
+    size_t s_scratch_cap = 0;
     size_t s_pcm_cap = 0, s_out_db_cap = 0, s_out_points_cap = 0, s_rms_cap = 0, s_peak_cap = 0, s_skip_cap = 0,
            s_silent_cap = 0;
     // copy/compute pipeline for host-pointer batches
@@ -162,7 +164,7 @@ bool supported_fft_size(int n)
     AnyPlan pl;
     if(!make_any_plan(n, &pl))
         return false;
-    return (size_t)pl.M * 16 + 8192 <= 220 * 1024 && (n & (n - 1)) != 0;
+    return n <= 65536; // sizes whose work buffers exceed shared memory run from a global (L2) scratch
 }
 
 bool is_device_ptr(const void *p)
@@ -217,7 +219,17 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     AnyPlan plan;
     if(!make_any_plan(e->tab.N, &plan))
         return set_err(e, WF_ERR_UNSUPPORTED_FFT_SIZE, "fft_size %d has no kernel", e->tab.N);
-    const size_t smem = (size_t)plan.M * 16 + extra;
+    const bool in_smem = (size_t)plan.M * 16 + extra <= 200 * 1024;
+    int grid = std::min(kp.n_streams, e->sm_count * (in_smem ? 8 : 2));
+    size_t smem = in_smem ? (size_t)plan.M * 16 + extra : extra;
+    plan.scratch = nullptr;
+    if(!in_smem)
+    {
+        int rc = ensure(e, &e->s_scratch, &e->s_scratch_cap, (size_t)grid * 2 * plan.M * 2);
+        if(rc)
+            return rc;
+        plan.scratch = reinterpret_cast<float2 *>(e->s_scratch);
+    }
     static thread_local size_t configured[8] = {0};
     const int dev = e->device & 7;
     if(smem > 48 * 1024 && configured[dev] < smem)
@@ -225,7 +237,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         WF_CUDA(e, cudaFuncSetAttribute(stft_anyn_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    stft_anyn_kernel<CC><<<kp.n_streams, kAnyThreads, smem, st>>>(kp, plan);
+    stft_anyn_kernel<CC><<<grid, kAnyThreads, smem, st>>>(kp, plan);
     WF_CUDA(e, cudaGetLastError());
     e->launches++;
     return WF_OK;
@@ -400,7 +412,7 @@ const char *wf_strerror(int status)
     {
     case WF_OK: return "ok";
     case WF_ERR_INVALID_ARG: return "invalid argument";
-    case WF_ERR_UNSUPPORTED_FFT_SIZE: return "unsupported fft_size (supported: multiples of 16 from 128; powers of two up to 32768, others up to ~27000)";
+    case WF_ERR_UNSUPPORTED_FFT_SIZE: return "unsupported fft_size (supported: multiples of 16 from 128 to 65536)";
     case WF_ERR_CUDA: return "CUDA error";
     case WF_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU fallback)";
     case WF_ERR_OOM: return "out of device memory";
@@ -569,7 +581,7 @@ void wf_destroy(wf_engine *e)
     }
     void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
-                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent};
+                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch};
     for(void *p : ptrs)
         if(p)
             cudaFree(p);
