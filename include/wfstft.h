@@ -89,6 +89,11 @@ typedef struct wf_config {
     int32_t interp_mode;       /* wf_interp, m_interp_mode */
     int32_t filter_mode;       /* wf_filter, m_filter_mode */
     float filter_radius;       /* m_filter_radius */
+    /* display stage (src/source.cpp:1408-1424, 1473-1565): dB -> pixel height of curve points / bars */
+    int32_t height;            /* m_height (after the radial adjustment, if any) */
+    int32_t channel_spacing;   /* m_channel_spacing (get_settings zeroes it unless stereo, src/source.cpp:579-580) */
+    int32_t rounded_caps;      /* m_rounded_caps (bars only) */
+    int32_t min_bar_height;    /* m_min_bar_height */
 } wf_config;
 
 /* Facts derived at create time. */
@@ -140,6 +145,9 @@ typedef struct wf_batch {
     uint8_t *out_silent;       /* optional [n_streams][n_frames] m_last_silent after the tick */
     float *out_peak;           /* optional [n_frames]: max over streams/channels/bins>=1 of the dB output
                                   (input to the cross-channel peak normalisation; all-reduce(max) it across GPUs) */
+    float *out_pixels;         /* optional [n_streams][n_frames][display_channels][num_points]: what render_curve /
+                                  render_bars leave in m_interp_bufs — pixel heights after lerp/clamp and mirroring */
+    float *out_min;            /* optional [n_streams][n_frames][2]: (miny, minpos) of the tick (pulse colouring) */
 } wf_batch;
 
 typedef struct wf_engine wf_engine;

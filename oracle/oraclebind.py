@@ -34,6 +34,7 @@ class WfoConfig(C.Structure):
         ("width", C.c_int32), ("bar_width", C.c_int32), ("bar_gap", C.c_int32),
         ("log_scale", C.c_int32), ("mirror_freq_axis", C.c_int32),
         ("interp_mode", C.c_int32), ("filter_mode", C.c_int32), ("filter_radius", C.c_float),
+        ("height", C.c_int32), ("channel_spacing", C.c_int32), ("rounded_caps", C.c_int32), ("min_bar_height", C.c_int32),
     ]
 
 
@@ -78,6 +79,9 @@ def lib():
     L.wfo_set_state.argtypes = [vp, C.c_int, f32p, f32p]
     L.wfo_interp.argtypes = [vp, C.c_int, f32p]
     L.wfo_run_stft.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, C.POINTER(C.c_ubyte)]
+    L.wfo_run_stft_px.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, C.POINTER(C.c_ubyte),
+                                  f32p, f32p]
+    L.wfo_render_pixels.argtypes = [vp, f32p, f32p, f32p]
     L.wfo_r2c.argtypes = [f32p, C.c_int, f32p]
     _lib = L
     return L
@@ -104,6 +108,8 @@ def config_from_settings(settings: dict | None = None, sample_rate=48000, channe
         "normalize_volume": "normalize_volume", "volume_target": "volume_target", "max_gain": "max_gain",
         "width": "width", "bar_width": "bar_width", "bar_gap": "bar_gap", "log_scale": "log_scale",
         "mirror_freq_axis": "mirror_freq_axis", "filter_radius": "filter_radius", "silence_gate": "silence_gate",
+        "height": "height", "channel_spacing": "channel_spacing", "rounded_caps": "rounded_caps",
+        "min_bar_height": "min_bar_height",
     }
     enums = {"window": ("window", WINDOWS), "interp_mode": ("interp_mode", INTERPS),
              "filter_mode": ("filter_mode", FILTERS), "temporal_smoothing": ("tsmoothing", TSMOOTH),
@@ -116,7 +122,7 @@ def config_from_settings(settings: dict | None = None, sample_rate=48000, channe
         elif k in enums:
             field, table = enums[k]
             setattr(c, field, table.get(v, 0))
-        elif k in ("height", "auto_fft_size", "audio_sync_offset"):
+        elif k in ("auto_fft_size", "audio_sync_offset"):
             pass
         else:
             raise KeyError(f"unsupported setting for the oracle: {k}")
@@ -244,6 +250,27 @@ class OracleSource:
                 self.L.wfo_set_state(self.h, ch, None, _fp(row))
                 self.L.wfo_interp(self.h, ch, _fp(out[i, ch]))
         return out.reshape(*lead, flat.shape[1], self.num_points)
+
+    def render_pixels(self):
+        """Pixel heights render_curve / render_bars would leave in m_interp_bufs for the current m_decibels, + (miny, minpos)."""
+        out = np.zeros((self.display_channels, self.num_points), dtype=np.float32)
+        miny, minpos = C.c_float(0), C.c_float(0)
+        self.L.wfo_render_pixels(self.h, _fp(out), C.byref(miny), C.byref(minpos))
+        return out, miny.value, minpos.value
+
+    def pixels_of(self, db):
+        """(pixels[..., dch, P], min[..., 2]) for GIVEN dB spectra db[..., dch, B]."""
+        db = np.ascontiguousarray(db, dtype=np.float32)
+        lead = db.shape[:-2]
+        flat = db.reshape(-1, db.shape[-2], db.shape[-1])
+        px = np.zeros((flat.shape[0], flat.shape[1], self.num_points), dtype=np.float32)
+        mn = np.zeros((flat.shape[0], 2), dtype=np.float32)
+        for i in range(flat.shape[0]):
+            for ch in range(flat.shape[1]):
+                self.L.wfo_set_state(self.h, ch, None, _fp(np.ascontiguousarray(flat[i, ch])))
+            p, a, b = self.render_pixels()
+            px[i], mn[i] = p, (a, b)
+        return px.reshape(*lead, flat.shape[1], self.num_points), mn.reshape(*lead, 2)
 
     def run_stft(self, pcm, n_frames, hop, seconds=1.0 / 60.0, rms=None, want_db=True, want_points=False):
         pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)

@@ -276,6 +276,10 @@ void wfo_config_defaults(wfo_config *c)
     c->interp_mode = WFO_INTERP_CATROM;
     c->filter_mode = WFO_FILTER_NONE;
     c->filter_radius = 1.5f;
+    c->height = 225;
+    c->channel_spacing = 0;
+    c->rounded_caps = 0;
+    c->min_bar_height = 0;
 }
 
 /* make_gauss_kernel, src/filter.hpp:40-65 */
@@ -442,6 +446,12 @@ wfo_source *wfo_create(const wfo_config *cfg_in)
         c->ceiling_db = 0;
         c->floor_db = -120;
     }
+    if(c->height < 1)
+        c->height = 225;
+    if(!c->stereo || ((int)c->height - c->channel_spacing) < 1) /* src/source.cpp:579-580 */
+        c->channel_spacing = 0;
+    if(c->display_mode != WFO_DISPLAY_BAR) /* src/source.cpp:655-656 */
+        c->rounded_caps = 0;
     if(c->capture_channels < 1)
         c->capture_channels = 1;
     if(c->capture_channels > 2)
@@ -879,6 +889,95 @@ int wfo_interp(wfo_source *s, int ch, float *out)
     if(out)
         memcpy(out, a, sizeof(float) * (size_t)npts);
     return npts;
+}
+
+void wfo_render_pixels(wfo_source *s, float *out, float *miny_out, float *minpos_out)
+{
+    const wfo_config *c = &s->cfg;
+    const int npts = wfo_num_points(s);
+    const int dch = wfo_display_channels(s);
+    const float center = (float)c->height / 2;
+    const float bottom = (float)c->height;
+    const int dbrange = c->ceiling_db - c->floor_db;
+    const float cpos = c->stereo ? center : bottom;
+    const float channel_offset = c->channel_spacing * 0.5f;
+    float lo, hi;
+    if(c->display_mode == WFO_DISPLAY_CURVE)
+    {
+        lo = 0.0f; /* src/source.cpp:1410 */
+        hi = cpos - channel_offset;
+    }
+    else
+    {
+        /* src/source.cpp:1481-1493 */
+        const float cap_radius = (float)c->bar_width / 2.0f; /* :1297 */
+        float border_top = c->rounded_caps ? cap_radius : 0.0f;
+        float border_bottom = (c->rounded_caps && (!c->stereo || (c->channel_spacing > 0))) ? cpos - cap_radius : cpos;
+        if(c->channel_spacing > 0)
+            border_bottom -= channel_offset;
+        if(c->min_bar_height > 0)
+            border_bottom -= c->min_bar_height;
+        border_bottom = clamp_f(border_bottom, border_top, cpos);
+        lo = border_top;
+        hi = border_bottom;
+    }
+    float miny = cpos;
+    unsigned minpos = 0u;
+    for(int channel = 0; channel < dch; ++channel)
+    {
+        float *buf = out + (size_t)channel * npts;
+        wfo_interp(s, channel, buf);
+        for(int i = 0; i < npts; ++i)
+        {
+            /* src/source.cpp:1408-1417, :1548-1557 */
+            const float val = lerp_f(lo, hi, clamp_f(c->ceiling_db - buf[i], 0.0f, (float)dbrange) / dbrange);
+            if(val < miny)
+            {
+                miny = val;
+                minpos = (unsigned)i;
+            }
+            buf[i] = val;
+        }
+        if(c->mirror_freq_axis)
+        {
+            /* src/source.cpp:1419-1424, :1559-1564 */
+            const unsigned half = (unsigned)npts / 2u;
+            for(unsigned i = half + 1; i < (unsigned)npts; ++i)
+                buf[i] = buf[half - (i - half)];
+        }
+    }
+    if(miny_out)
+        *miny_out = miny;
+    if(minpos_out)
+        *minpos_out = (float)minpos;
+}
+
+int wfo_run_stft_px(wfo_source *s, const float *pcm0, const float *pcm1, int n_frames, int hop, float seconds,
+                    const float *input_rms, float *out_db, float *out_points, unsigned char *out_silent,
+                    float *out_pixels, float *out_min)
+{
+    const int dch = wfo_display_channels(s);
+    const size_t B = (size_t)s->B;
+    const int npts = wfo_num_points(s);
+    for(int t = 0; t < n_frames; ++t)
+    {
+        const float *frames[2];
+        frames[0] = pcm0 + (size_t)t * (size_t)hop;
+        frames[1] = pcm1 ? pcm1 + (size_t)t * (size_t)hop : NULL;
+        wfo_tick(s, frames, seconds, input_rms ? input_rms[t] : 0.0f);
+        if(out_db)
+            for(int ch = 0; ch < dch; ++ch)
+                memcpy(out_db + ((size_t)t * dch + ch) * B, s->decibels[ch], B * sizeof(float));
+        if(out_points)
+            for(int ch = 0; ch < dch; ++ch)
+                wfo_interp(s, ch, out_points + ((size_t)t * dch + ch) * (size_t)npts);
+        if(out_pixels)
+            wfo_render_pixels(s, out_pixels + (size_t)t * dch * (size_t)npts, out_min ? out_min + 2 * t : NULL,
+                              out_min ? out_min + 2 * t + 1 : NULL);
+        if(out_silent)
+            out_silent[t] = (unsigned char)s->last_silent;
+    }
+    return n_frames;
 }
 
 int wfo_run_stft(wfo_source *s, const float *pcm0, const float *pcm1, int n_frames, int hop, float seconds,

@@ -52,6 +52,7 @@ typedef struct wfo_config {
     int32_t interp_mode;
     int32_t filter_mode;
     float filter_radius;
+    int32_t height, channel_spacing, rounded_caps, min_bar_height; /* display stage */
 } wfo_config;
 
 typedef struct wfo_source wfo_source; /* one WAVSource worth of state */
@@ -91,10 +92,19 @@ void wfo_set_state(wfo_source *s, int ch, const float *tsmooth, const float *dec
  * src/source.cpp:1381-1406,1510-1546; src/filter.hpp:133-211.  Returns points written. */
 int wfo_interp(wfo_source *s, int ch, float *out);
 
+/* The rest of render_curve / render_bars up to (excluding) vertex generation: interpolation + Gaussian for every display
+ * channel, dB -> pixel lerp/clamp with the running (miny, minpos), then frequency-axis mirroring.
+ * out: [display_channels][points]; src/source.cpp:1376-1425 (curve), :1481-1565 (bars). */
+void wfo_render_pixels(wfo_source *s, float *out, float *miny, float *minpos);
+
 /* Sliding STFT of one source: frame t = pcm[c][t*hop .. t*hop+N).  Layouts as the engine's:
  * out_db [n_frames][display_channels][bins], out_points [n_frames][display_channels][points]. */
 int wfo_run_stft(wfo_source *s, const float *pcm0, const float *pcm1, int n_frames, int hop, float seconds,
                  const float *input_rms, float *out_db, float *out_points, unsigned char *out_silent);
+/* same, additionally out_pixels [n_frames][display_channels][points] and out_min [n_frames][2] */
+int wfo_run_stft_px(wfo_source *s, const float *pcm0, const float *pcm1, int n_frames, int hop, float seconds,
+                    const float *input_rms, float *out_db, float *out_points, unsigned char *out_silent,
+                    float *out_pixels, float *out_min);
 
 /* The bare transform restated on its own (forward unnormalised r2c, N/2+1 outputs interleaved),
  * deps/fftw-3.3.11/doc/reference.texi:1926-1936, api/plan-dft-r2c-1d.c:23-26. Any N >= 2. */

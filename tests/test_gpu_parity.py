@@ -294,3 +294,31 @@ def test_subwarp_groups_diverge_independently(N):
     assert parity_report(got, ref_db, db_min=eng.db_min)["ok"]
     assert np.allclose(out["peak"].cpu().numpy(), got[..., 1:].max(axis=(0, 2, 3)))
     assert check_points(settings, 1, got, out["points"].cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("settings,channels", [
+    ({"fft_size": 1024, "display_mode": "curve", "interp_mode": "lanczos", "height": 300}, 1),
+    ({"fft_size": 2048, "display_mode": "bars", "interp_mode": "catmull_rom", "rounded_caps": True, "min_bar_height": 5,
+      "bar_width": 10, "bar_gap": 2}, 1),
+    ({"fft_size": 1024, "display_mode": "curve", "channel_mode": "stereo", "channel_spacing": 20, "mirror_freq_axis": True,
+      "filter_mode": "gauss", "height": 400}, 2),
+    ({"fft_size": 4096, "display_mode": "bars", "channel_mode": "stereo", "channel_spacing": 10, "rounded_caps": True,
+      "mirror_freq_axis": True, "interp_mode": "point"}, 2),
+    ({"fft_size": 800, "display_mode": "curve", "interp_mode": "catmull_rom", "height": 225}, 1),
+])
+def test_display_stage_pixels(settings, channels):
+    """dB -> pixel heights, mirroring and (miny, minpos) in the kernel epilogue, against the oracle's
+    restatement of render_curve / render_bars (itself checked against WAVSource::render in test_oracle_vs_reference)."""
+    from oracle.oraclebind import OracleSource
+    S, T = 4, 6
+    eng = _engine(settings, channels, S)
+    N = eng.fft_size
+    pcm = synth_pcm(S, eng.capture_channels, T * N)
+    out = eng.process(pcm, T, N, want_points=True, want_pixels=True)
+    o = OracleSource(settings, channels=channels)
+    exp_px, exp_min = o.pixels_of(out["db"])
+    assert np.abs(out["pixels"] - exp_px).max() < 2e-4, float(np.abs(out["pixels"] - exp_px).max())
+    assert np.abs(out["min"][..., 0] - exp_min[..., 0]).max() < 2e-4
+    same = out["min"][..., 1] == exp_min[..., 1]
+    assert same.mean() > 0.9  # an exact tie between two points can flip under a 1e-5 px difference
+    assert check_points(settings, channels, out["db"], out["points"]) < 2e-6

@@ -80,3 +80,38 @@ def test_av_sync_offset_selects_older_frame():
     o = OracleSource({k: v for k, v in s.items() if k != "audio_sync_offset"}, channels=1)
     o.tick([x[0, -N:]])
     assert parity_report(latest, o.decibels(0))["ok"]
+
+
+PX_CASES = [
+    ({"fft_size": 1024, "display_mode": "curve", "interp_mode": "lanczos", "height": 300}, 1),
+    ({"fft_size": 2048, "display_mode": "bars", "interp_mode": "catmull_rom", "rounded_caps": True, "min_bar_height": 5,
+      "bar_width": 10, "bar_gap": 2}, 1),
+    ({"fft_size": 1024, "display_mode": "curve", "channel_mode": "stereo", "channel_spacing": 20, "mirror_freq_axis": True,
+      "filter_mode": "gauss", "height": 400}, 2),
+    ({"fft_size": 1024, "display_mode": "bars", "channel_mode": "stereo", "channel_spacing": 10, "rounded_caps": True,
+      "mirror_freq_axis": True, "interp_mode": "point"}, 2),
+]
+
+
+@pytest.mark.parametrize("settings,channels", PX_CASES)
+def test_display_stage_matches_reference_render(settings, channels):
+    """dB -> pixel lerp/clamp, mirroring and (miny, minpos): the oracle against WAVSource::render() itself
+    (src/source.cpp:1346-1565 run verbatim behind the fake graphics API)."""
+    ref = refbind.RefSource(settings, impl=refbind.IMPL_GENERIC, channels=channels)
+    orc = OracleSource(settings, channels=channels)
+    N, T = ref.fft_size, 6
+    x = synth_pcm(1, ref.capture_channels, T * N, seed=4)[0]
+    for t in range(T):
+        ref.advance(N / 48000)
+        ref.push(x[0, t * N:(t + 1) * N], x[1, t * N:(t + 1) * N] if ref.capture_channels > 1 else None)
+        ref.tick()
+        orc.tick([x[c, t * N:(t + 1) * N] for c in range(ref.capture_channels)])
+    ref.render()
+    px, miny, minpos = orc.render_pixels()
+    for c in range(ref.display_channels):
+        assert np.abs(ref.render_buf(c) - px[c]).max() < 5e-4
+    # fed with the reference's own m_decibels only the interpolation's summation order differs: on an AVX machine
+    # render() takes apply_interp_filter_fma3 (src/source.cpp:1383-1387), the oracle restates the generic template
+    px2, _ = orc.pixels_of(np.stack([ref.decibels(c) for c in range(ref.display_channels)]))
+    for c in range(ref.display_channels):
+        assert np.abs(ref.render_buf(c) - px2[c]).max() < 1e-4

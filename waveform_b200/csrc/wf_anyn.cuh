@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
     float2 *bufB = bufA + M;
     // [dch][n_points] intermediate of the Gaussian (only when filtering display points)
     float *pts = (plan.scratch != nullptr) ? reinterpret_cast<float *>(smem_raw) : reinterpret_cast<float *>(bufB + M);
-    __shared__ float red_scratch[32];
+    __shared__ float red_scratch[2 * kAnyThreads];
     const int tid = threadIdx.x;
     const int dch = p.dch, och = p.och;
     const bool stereo = p.stereo != 0;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
         }
         float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * T + t) * dch * B : nullptr;
         const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
-        const bool want_points = p.out_points != nullptr;
+        const bool want_points = (p.out_points != nullptr) || (p.out_pixels != nullptr) || (p.out_min != nullptr);
         float *dbs = reinterpret_cast<float *>(bufA); // dB spectrum [dch][B] for the display stage (2B floats fit)
         float peak = -INFINITY;
         bool outs0 = true, outs1 = true;
@@ -243,25 +243,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
         if(want_points)
         {
             __syncthreads();
-            float *opt = p.out_points + ((size_t)s * T + t) * dch * p.n_points;
-            for(int d = 0; d < dch; ++d)
-            {
-                const float *db = dbs + d * B;
-                if(!p.filter)
-                {
-                    for(int i = tid; i < p.n_points; i += kAnyThreads)
-                        stg_stream(opt + d * p.n_points + i, interp_point(p, db, B, i));
-                }
-                else
-                {
-                    float *pp = pts + d * p.n_points;
-                    for(int i = tid; i < p.n_points; i += kAnyThreads)
-                        pp[i] = interp_point(p, db, B, i);
-                    __syncthreads();
-                    for(int i = tid; i < p.n_points; i += kAnyThreads)
-                        stg_stream(opt + d * p.n_points + i, weighted_avg(p, pp, p.n_points, i));
-                }
-            }
+            display_stage<kAnyThreads>(p, dbs, pts, B, dch, (size_t)s * T + t, tid, true, red_scratch);
         }
     }
 

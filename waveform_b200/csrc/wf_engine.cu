@@ -53,6 +53,8 @@ struct wf_engine {
     // staging for host-pointer batches (grown on demand)
     float *s_pcm = nullptr, *s_out_db = nullptr, *s_out_points = nullptr, *s_rms = nullptr, *s_peak = nullptr;
     unsigned char *s_skip = nullptr, *s_silent = nullptr;
+    float *s_px = nullptr, *s_min = nullptr;
+    size_t s_px_cap = 0, s_min_cap = 0;
     float *s_scratch = nullptr; // any-N kernel work buffers when N/2 complex points x 2 exceed shared memory
     size_t s_scratch_cap = 0;
     size_t s_pcm_cap = 0, s_out_db_cap = 0, s_out_points_cap = 0, s_rms_cap = 0, s_peak_cap = 0, s_skip_cap = 0,
@@ -460,6 +462,10 @@ void wf_config_init(wf_config *c)
     c->interp_mode = WF_INTERP_CATROM;
     c->filter_mode = WF_FILTER_NONE;
     c->filter_radius = 1.5f;
+    c->height = 225;
+    c->channel_spacing = 0;
+    c->rounded_caps = 0;
+    c->min_bar_height = 0;
 }
 
 int wf_create(const wf_config *cfg, wf_engine **out)
@@ -581,7 +587,7 @@ void wf_destroy(wf_engine *e)
     }
     void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
-                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch};
+                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min};
     for(void *p : ptrs)
         if(p)
             cudaFree(p);
@@ -692,7 +698,7 @@ int64_t wf_preview_table(const wf_config *cfg, int which, float *out, int64_t ca
 // offset to stream 0 of the batch.
 static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0, int count, const float *pcm,
                         const float *rms, const unsigned char *skip, float *out_db, float *out_points,
-                        unsigned char *silent, float *out_peak)
+                        unsigned char *silent, float *out_peak, float *px_dev, float *min_dev)
 {
     const Tables &t = e->tab;
     const int cc = t.cfg.capture_channels, dch = t.display_channels, och = t.output_channels, B = t.B, N = t.N;
@@ -751,10 +757,18 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     kp.gauss_size = (int)t.gauss.size();
     kp.gauss_sum = t.gauss_sum;
     kp.filter = (t.cfg.filter_mode == WF_FILTER_GAUSS);
+    kp.out_pixels = b->out_pixels ? px_dev + (size_t)s0 * T * dch * t.num_points : nullptr;
+    kp.out_min = b->out_min ? min_dev + (size_t)s0 * T * 2 : nullptr;
+    kp.px_lo = t.px_lo;
+    kp.px_hi = t.px_hi;
+    kp.px_cpos = t.px_cpos;
+    kp.ceiling_f = (float)t.cfg.ceiling_db;
+    kp.dbrange_f = (float)(t.cfg.ceiling_db - t.cfg.floor_db);
+    kp.mirror = t.cfg.mirror_freq_axis;
 
-    // shared memory for the gaussian intermediate: [groups][2][num_points] floats
+    // shared memory for the display stage: [groups][2][dch <= 2][num_points] floats
     size_t extra = 0;
-    if(kp.out_points && kp.filter)
+    if(kp.out_points || kp.out_pixels || kp.out_min)
     {
         int groups = 1;
         switch(N)
@@ -766,11 +780,11 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         case 2048: groups = Geo<2048>::GROUPS; break;
         default: groups = 1; break;
         }
-        extra = (size_t)groups * 2 * (size_t)t.num_points * sizeof(float);
+        extra = (size_t)groups * 4 * (size_t)t.num_points * sizeof(float);
     }
     const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
-    const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && aligned16 &&
-                         !e->force_generic;
+    const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&
+                         !kp.out_min && aligned16 && !e->force_generic;
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
@@ -798,8 +812,8 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         return set_err(e, WF_ERR_INVALID_ARG, "pcm is null");
     if(b->stream_stride < 0 || b->channel_stride < 0)
         return set_err(e, WF_ERR_INVALID_ARG, "negative strides are not supported");
-    if(b->out_points && t.num_points <= 0)
-        return set_err(e, WF_ERR_INVALID_ARG, "out_points requested but the engine has no display points");
+    if((b->out_points || b->out_pixels || b->out_min) && t.num_points <= 0)
+        return set_err(e, WF_ERR_INVALID_ARG, "display outputs requested but the engine has no display points");
 
     WF_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
@@ -816,7 +830,7 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
                 return rc;
         }
         int rc = launch_range(e, b, st, 0, b->n_streams, b->pcm, b->input_rms, b->skip_mask, b->out_db, b->out_points,
-                              b->out_silent, b->out_peak);
+                              b->out_silent, b->out_peak, b->out_pixels, b->out_min);
         if(rc)
             return rc;
         WF_CUDA(e, cudaEventRecord(e->ev1, st));
@@ -870,6 +884,19 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
             return rc;
         d_peak = e->s_peak;
     }
+    float *d_px = nullptr, *d_min = nullptr;
+    if(b->out_pixels)
+    {
+        if((rc = ensure(e, &e->s_px, &e->s_px_cap, S * T * dch * t.num_points)))
+            return rc;
+        d_px = e->s_px;
+    }
+    if(b->out_min)
+    {
+        if((rc = ensure(e, &e->s_min, &e->s_min_cap, S * T * 2)))
+            return rc;
+        d_min = e->s_min;
+    }
     if(!e->s_h2d)
     {
         WF_CUDA(e, cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
@@ -910,7 +937,8 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
                                        cudaMemcpyHostToDevice, e->s_h2d));
         WF_CUDA(e, cudaEventRecord(e->chunk_in[c], e->s_h2d));
         WF_CUDA(e, cudaStreamWaitEvent(st, e->chunk_in[c], 0));
-        if((rc = launch_range(e, b, st, s0, cnt, e->s_pcm, d_rms, d_skip, d_out_db, d_out_points, d_silent, d_peak)))
+        if((rc = launch_range(e, b, st, s0, cnt, e->s_pcm, d_rms, d_skip, d_out_db, d_out_points, d_silent, d_peak, d_px,
+                              d_min)))
             return rc;
         WF_CUDA(e, cudaEventRecord(e->chunk_k[c], st));
         WF_CUDA(e, cudaStreamWaitEvent(e->s_d2h, e->chunk_k[c], 0));
@@ -924,6 +952,13 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         if(b->out_silent)
             WF_CUDA(e, cudaMemcpyAsync(b->out_silent + (size_t)s0 * T, d_silent + (size_t)s0 * T, (size_t)cnt * T,
                                        cudaMemcpyDeviceToHost, e->s_d2h));
+        if(b->out_pixels)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_pixels + (size_t)s0 * T * dch * t.num_points,
+                                       d_px + (size_t)s0 * T * dch * t.num_points,
+                                       (size_t)cnt * T * dch * t.num_points * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
+        if(b->out_min)
+            WF_CUDA(e, cudaMemcpyAsync(b->out_min + (size_t)s0 * T * 2, d_min + (size_t)s0 * T * 2,
+                                       (size_t)cnt * T * 2 * sizeof(float), cudaMemcpyDeviceToHost, e->s_d2h));
     }
     WF_CUDA(e, cudaEventRecord(e->ev1, st));
     e->ev_valid = true;

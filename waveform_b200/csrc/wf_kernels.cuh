@@ -67,6 +67,14 @@ struct KParams {
     int gauss_radius, gauss_size;
     float gauss_sum;
     int filter;
+    // display stage (dB -> pixels)
+    float *out_pixels;     // [streams][frames][DCH][n_points] or null
+    float *out_min;        // [streams][frames][2] or null
+    float px_lo, px_hi;    // lerp endpoints: (0, cpos - channel_offset) for the curve, (border_top, border_bottom) for bars
+    float px_cpos;         // initial miny
+    float ceiling_f;       // (float)m_ceiling
+    float dbrange_f;       // (float)(m_ceiling - m_floor)
+    int mirror;
 };
 
 // ---- plans: threads per frame (TN) and per-pass radices for each supported N -----------------------
@@ -387,6 +395,121 @@ __device__ __forceinline__ float weighted_avg(const KParams &p, const float *sam
     return __fdiv_rn(sum, p.gauss_sum);
 }
 
+// std::lerp(float,float,float) as libstdc++ evaluates it (the plugin's lerp(), src/math_funcs.hpp:31-35), no contraction
+__device__ __forceinline__ float std_lerp_dev(float a, float b, float t)
+{
+    if((a <= 0.0f && b >= 0.0f) || (a >= 0.0f && b <= 0.0f))
+        return __fadd_rn(__fmul_rn(t, b), __fmul_rn(__fsub_rn(1.0f, t), a));
+    if(t == 1.0f)
+        return b;
+    const float x = __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+    return ((t > 1.0f) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+}
+
+// Render-time stages for one tick of one stream, from its dB spectrum `dbs` ([dch][B], shared or L2):
+//   interpolation to display points (src/filter.hpp:182-211, src/source.cpp:1392-1394,1523-1532)
+//   -> Gaussian smoothing (src/filter.hpp:133-180) -> out_points
+//   -> dB -> pixel height (lerp/clamp), running (miny, minpos), frequency-axis mirroring
+//      (src/source.cpp:1408-1424 curve, :1548-1565 bars) -> out_pixels / out_min
+// `pts` is scratch for [2][dch][n_points] floats.  TN threads (one group) cooperate; SYNC() is the group barrier.
+template<int TN>
+__device__ __forceinline__ void display_stage(const KParams &p, const float *dbs, float *pts, int B, int dch, size_t tick,
+                                              int tid, bool active, float *red)
+{
+    const int np = p.n_points;
+    const bool need_smem = p.filter || (p.out_pixels != nullptr) || (p.out_min != nullptr);
+    float *raw = pts;                 // interpolated points
+    float *fin = pts + dch * np;      // after the Gaussian (or alias of raw)
+    for(int d = 0; d < dch; ++d)
+    {
+        const float *db = dbs + d * B;
+        for(int i = tid; i < np; i += TN)
+        {
+            const float val = interp_point(p, db, B, i);
+            if(need_smem)
+                raw[d * np + i] = val;
+            else if(active)
+                stg_stream(p.out_points + (tick * dch + d) * np + i, val);
+        }
+    }
+    if(!need_smem)
+        return;
+    group_sync<TN>();
+    if(p.filter)
+    {
+        for(int d = 0; d < dch; ++d)
+            for(int i = tid; i < np; i += TN)
+                fin[d * np + i] = weighted_avg(p, raw + d * np, np, i);
+        group_sync<TN>();
+    }
+    else
+        fin = raw;
+    if(p.out_points != nullptr && active)
+        for(int i = tid; i < dch * np; i += TN)
+            stg_stream(p.out_points + tick * dch * np + i, fin[i]);
+    if(p.out_pixels == nullptr && p.out_min == nullptr)
+        return;
+    // dB -> pixels, in place; per-thread running minimum in (channel, index) order with strict '<'
+    float my_min = INFINITY;
+    int my_pos = 0x7fffffff;
+    for(int d = 0; d < dch; ++d)
+        for(int i = tid; i < np; i += TN)
+        {
+            const float c = fminf(fmaxf(__fsub_rn(p.ceiling_f, fin[d * np + i]), 0.0f), p.dbrange_f); // std::clamp
+            const float val = std_lerp_dev(p.px_lo, p.px_hi, __fdiv_rn(c, p.dbrange_f));
+            fin[d * np + i] = val;
+            if(val < my_min)
+            {
+                my_min = val;
+                my_pos = d * np + i;
+            }
+        }
+    // group arg-min (ties -> earliest (channel, index), as the sequential scan of the reference does)
+    red[2 * tid] = my_min;
+    red[2 * tid + 1] = __int_as_float(my_pos);
+    group_sync<TN>();
+    if(tid == 0 && p.out_min != nullptr && active)
+    {
+        float miny = p.px_cpos;
+        int minpos = 0;
+        float best = INFINITY;
+        int bpos = 0x7fffffff;
+        for(int k = 0; k < TN; ++k)
+        {
+            const float v = red[2 * k];
+            const int q = __float_as_int(red[2 * k + 1]);
+            if(v < best || (v == best && q < bpos))
+            {
+                best = v;
+                bpos = q;
+            }
+        }
+        // sequential semantics: miny starts at cpos and only a strictly smaller value replaces it; minpos is the index
+        // within its channel.  The reference resets nothing between channels, so a later channel wins only if smaller.
+        if(best < miny)
+        {
+            miny = best;
+            minpos = bpos % np;
+        }
+        p.out_min[tick * 2] = miny;
+        p.out_min[tick * 2 + 1] = (float)minpos;
+    }
+    if(p.mirror)
+    {
+        group_sync<TN>();
+        const int half = np / 2;
+        // i > half takes the value at half - (i - half); sources (< half) are never overwritten
+        for(int d = 0; d < dch; ++d)
+            for(int i = half + 1 + tid; i < np; i += TN)
+                fin[d * np + i] = fin[d * np + (half - (i - half))];
+        group_sync<TN>();
+    }
+    if(p.out_pixels != nullptr && active)
+        for(int i = tid; i < dch * np; i += TN)
+            stg_stream(p.out_pixels + tick * dch * np + i, fin[i]);
+    group_sync<TN>();
+}
+
 // ---- the fused kernel ------------------------------------------------------------------------------
 template<int N, int CC>
 __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_constant__ KParams p)
@@ -401,8 +524,8 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
     const int tid = threadIdx.x % TN;
     float2 *buf = smem + (size_t)grp * G::BUF;
     float *dbs = reinterpret_cast<float *>(buf); // dB spectrum [dch][B] overlays the exchange buffer
-    float *pts = reinterpret_cast<float *>(smem + (size_t)G::GROUPS * G::BUF) + (size_t)grp * 2 * p.n_points;
-    __shared__ float red_scratch[32];
+    float *pts = reinterpret_cast<float *>(smem + (size_t)G::GROUPS * G::BUF) + (size_t)grp * 4 * p.n_points;
+    __shared__ float red_scratch[2 * (G::CTA > 32 ? G::CTA : 32)];
 
     const int s_raw = blockIdx.x * G::GROUPS + grp;
     const bool active = s_raw < p.n_streams;
@@ -517,7 +640,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
         }
         float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * p.n_frames + t) * dch * B : nullptr;
         const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
-        const bool want_points = p.out_points != nullptr;
+        const bool want_points = (p.out_points != nullptr) || (p.out_pixels != nullptr) || (p.out_min != nullptr);
         if(want_points)
             group_sync<TN>(); // split-pass reads of buf are done before dB overwrites it
 
@@ -594,37 +717,11 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
                 atomic_max_float(p.out_peak + t, gm);
         }
 
-        // ---- display points: interpolation (+ gaussian) from the dB spectrum in shared memory ----
+        // ---- render-time stages from the dB spectrum in shared memory ----
         if(want_points)
         {
             group_sync<TN>();
-            float *opt = p.out_points + ((size_t)s * p.n_frames + t) * dch * p.n_points;
-            for(int d = 0; d < dch; ++d)
-            {
-                const float *db = dbs + d * B;
-                if(!p.filter)
-                {
-                    for(int i = tid; i < p.n_points; i += TN)
-                    {
-                        const float val = interp_point(p, db, B, i);
-                        if(active)
-                            stg_stream(opt + d * p.n_points + i, val);
-                    }
-                }
-                else
-                {
-                    float *pp = pts + d * p.n_points;
-                    for(int i = tid; i < p.n_points; i += TN)
-                        pp[i] = interp_point(p, db, B, i);
-                    group_sync<TN>();
-                    for(int i = tid; i < p.n_points; i += TN)
-                    {
-                        const float val = weighted_avg(p, pp, p.n_points, i);
-                        if(active)
-                            stg_stream(opt + d * p.n_points + i, val);
-                    }
-                }
-            }
+            display_stage<TN>(p, dbs, pts, B, dch, (size_t)s * p.n_frames + t, tid, active, red_scratch + grp * 2 * TN);
         }
     }
 

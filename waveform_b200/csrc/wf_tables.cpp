@@ -359,6 +359,39 @@ int build_tables(const wf_config &cfg_in, Tables &t, const char **why)
         build_interp(t, (unsigned)(t.num_bars + 1)); // extra band for the last bar
     }
 
+    // display geometry, src/source.cpp:579-580 (spacing), :655-656 (caps), :1365-1373 (curve), :1481-1493 (bars)
+    if(c.height < 1)
+        c.height = 225;
+    if(!c.stereo || (c.height - c.channel_spacing) < 1)
+        c.channel_spacing = 0;
+    if(c.display_mode != WF_DISPLAY_BAR)
+        c.rounded_caps = 0;
+    {
+        const auto center = (float)c.height / 2;
+        const auto bottom = (float)c.height;
+        const auto cpos = c.stereo ? center : bottom;
+        const auto channel_offset = c.channel_spacing * 0.5f;
+        t.px_cpos = cpos;
+        if(c.display_mode == WF_DISPLAY_CURVE)
+        {
+            t.px_lo = 0.0f;
+            t.px_hi = cpos - channel_offset;
+        }
+        else
+        {
+            const float cap_radius = (float)c.bar_width / 2.0f;
+            auto border_top = c.rounded_caps ? cap_radius : 0.0f;
+            auto border_bottom = (c.rounded_caps && (!c.stereo || (c.channel_spacing > 0))) ? cpos - cap_radius : cpos;
+            if(c.channel_spacing > 0)
+                border_bottom -= channel_offset;
+            if(c.min_bar_height > 0)
+                border_bottom -= c.min_bar_height;
+            border_bottom = std::clamp(border_bottom, border_top, cpos);
+            t.px_lo = border_top;
+            t.px_hi = border_bottom;
+        }
+    }
+
     build_gauss(t);
     build_slope(t);
     build_rolloff(t);

@@ -26,6 +26,8 @@ struct Tables {
     int num_points = 0;
     float window_sum = 1.0f; // m_window_sum
     float db_min = 0.0f;     // DB_MIN (src/source.cpp:43)
+    // display stage: lerp endpoints and initial miny of render_curve / render_bars (src/source.cpp:1365-1373,1481-1493)
+    float px_lo = 0.0f, px_hi = 0.0f, px_cpos = 0.0f;
 
     std::vector<float> window;         // m_window_coefficients (empty = none)
     std::vector<float> slope;          // m_slope_modifiers (empty = off)

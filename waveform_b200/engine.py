@@ -58,6 +58,7 @@ class WfConfig(C.Structure):
         ("width", C.c_int32), ("bar_width", C.c_int32), ("bar_gap", C.c_int32),
         ("log_scale", C.c_int32), ("mirror_freq_axis", C.c_int32),
         ("interp_mode", C.c_int32), ("filter_mode", C.c_int32), ("filter_radius", C.c_float),
+        ("height", C.c_int32), ("channel_spacing", C.c_int32), ("rounded_caps", C.c_int32), ("min_bar_height", C.c_int32),
     ]
 
 
@@ -77,6 +78,7 @@ class WfBatch(C.Structure):
         ("pcm", C.c_void_p), ("stream_stride", C.c_int64), ("channel_stride", C.c_int64),
         ("input_rms", C.c_void_p), ("skip_mask", C.c_void_p),
         ("out_db", C.c_void_p), ("out_points", C.c_void_p), ("out_silent", C.c_void_p), ("out_peak", C.c_void_p),
+        ("out_pixels", C.c_void_p), ("out_min", C.c_void_p),
     ]
 
 
@@ -151,6 +153,8 @@ def make_config(settings: dict | None = None, sample_rate: int = 48000, channels
         "normalize_volume": "normalize_volume", "volume_target": "volume_target", "max_gain": "max_gain",
         "width": "width", "bar_width": "bar_width", "bar_gap": "bar_gap", "log_scale": "log_scale",
         "mirror_freq_axis": "mirror_freq_axis", "filter_radius": "filter_radius", "silence_gate": "silence_gate",
+        "height": "height", "channel_spacing": "channel_spacing", "rounded_caps": "rounded_caps",
+        "min_bar_height": "min_bar_height",
     }
     enums = {"window": ("window", WINDOWS), "interp_mode": ("interp_mode", INTERPS),
              "filter_mode": ("filter_mode", FILTERS), "temporal_smoothing": ("tsmoothing", TSMOOTH),
@@ -165,7 +169,7 @@ def make_config(settings: dict | None = None, sample_rate: int = 48000, channels
             if v not in table:
                 raise ValueError(f"{k}={v!r} is not a spectrum-mode value")
             setattr(c, field, table[v])
-        elif k in ("height", "auto_fft_size", "audio_sync_offset"):
+        elif k in ("auto_fft_size", "audio_sync_offset"):
             pass  # display / capture plumbing that stays on the host side of the seam
         else:
             raise KeyError(f"setting {k!r} is outside the spectrum hot path")
@@ -287,7 +291,7 @@ class Engine:
     # ---- processing ----
     def process_raw(self, pcm_ptr, n_streams, n_frames, hop, stream_stride, channel_stride, *, first_stream=0,
                     seconds=1.0 / 60.0, input_rms=None, skip_mask=None, out_db=None, out_points=None,
-                    out_silent=None, out_peak=None, stream=None, sync=True):
+                    out_silent=None, out_peak=None, out_pixels=None, out_min=None, stream=None, sync=True):
         """Thin wrapper over wf_process / wf_process_async with raw pointers (ints)."""
         b = WfBatch()
         b.struct_size = C.sizeof(WfBatch)
@@ -297,6 +301,7 @@ class Engine:
         b.stream_stride, b.channel_stride = stream_stride, channel_stride
         b.input_rms, b.skip_mask = input_rms, skip_mask
         b.out_db, b.out_points, b.out_silent, b.out_peak = out_db, out_points, out_silent, out_peak
+        b.out_pixels, b.out_min = out_pixels, out_min
         if sync and stream is None:
             self._check(self.L.wf_process(self.h, C.byref(b)))
         else:
@@ -305,7 +310,7 @@ class Engine:
             self._check(self.L.wf_process_async(self.h, C.byref(b), stream))
 
     def process(self, pcm, n_frames: int, hop: int, *, first_stream=0, seconds=1.0 / 60.0, input_rms=None,
-                skip_mask=None, want_db=True, want_points=False, want_silent=True, want_peak=False):
+                skip_mask=None, want_db=True, want_points=False, want_silent=True, want_peak=False, want_pixels=False):
         """pcm: [n_streams, capture_channels, samples] float32 — numpy (host path, staged inside the C call)
         or a CUDA torch tensor (device path, outputs are CUDA tensors)."""
         is_torch = hasattr(pcm, "data_ptr")
@@ -344,10 +349,13 @@ class Engine:
             out["silent"] = mk((S, n_frames), u8)
         if want_peak:
             out["peak"] = mk((n_frames,), f32)
+        if want_pixels:
+            out["pixels"] = mk((S, n_frames, dch, P), f32)
+            out["min"] = mk((S, n_frames, 2), f32)
         self.process_raw(_ptr(pcm), S, n_frames, hop, cc * ns, ns, first_stream=first_stream, seconds=seconds,
                          input_rms=_ptr(input_rms), skip_mask=_ptr(skip_mask), out_db=_ptr(out.get("db")),
                          out_points=_ptr(out.get("points")), out_silent=_ptr(out.get("silent")),
-                         out_peak=_ptr(out.get("peak")))
+                         out_peak=_ptr(out.get("peak")), out_pixels=_ptr(out.get("pixels")), out_min=_ptr(out.get("min")))
         return out
 
     def synchronize(self):
