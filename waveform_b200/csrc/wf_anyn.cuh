@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
                     const float2 dif = csub(a, b);
                     const float2 o = make_float2(dif.y, -dif.x);
                     const float2 y = cadd(sum, cmul(o, __ldg(p.tw_post + k)));
-                    float mag = sqrtf(fmaf(y.x, y.x, y.y * y.y)) * p.coef_half;
+                    float mag = sqrt_mufu(fmaf(y.x, y.x, y.y * y.y)) * p.coef_half;
                     if(p.slope != nullptr)
                         mag *= __ldg(p.slope + k);
                     if(p.tsmooth)
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
                         const int c = (CC == 2) ? d : 0;
                         in = proc[c] ? state_s[(size_t)c * B + k] : prev_db[c * B + k];
                     }
-                    outv = dbfs(in, p.db_min);
+                    outv = dbfs_mufu(in, p.db_min);
                     if(k >= 1)
                     {
                         if(p.normalize)

@@ -195,10 +195,23 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v)
         atomicMin((unsigned int *)addr, __float_as_uint(v));
 }
 
-// dbfs, src/source.hpp:293-299
+// dbfs, src/source.hpp:293-299 (libm-accurate form; used on rare paths and per-tick scalars)
 __device__ __forceinline__ float dbfs(float mag, float db_min)
 {
     return (mag > 0.0f) ? 20.0f * log10f(mag) : db_min;
+}
+// dbfs on the MUFU.LG2 path for the per-bin hot loops: 20 log10(m) = (20 log10 2) log2(m).  __log2f rescales
+// subnormal inputs, so the reference's behaviour is kept over the whole float range (<= 2 ulp of log2).
+__device__ __forceinline__ float dbfs_mufu(float mag, float db_min)
+{
+    return (mag > 0.0f) ? __log2f(mag) * 6.02059991327962390f : db_min;
+}
+// sqrt on the MUFU path (subnormal-safe variant, max relative error 2^-23)
+__device__ __forceinline__ float sqrt_mufu(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // ---- Stockham passes -------------------------------------------------------------------------------
@@ -228,23 +241,23 @@ struct Pass {
         for(int b = 0; b < BPT; ++b)
         {
             const int j = tid + b * TN;
-            float2 x[R];
+            pk::c64 x[R]; // packed f32x2 complex arithmetic: FADD2 / FMUL2 / FFMA2 (see wf_fft.cuh)
 #pragma unroll
             for(int t = 0; t < R; ++t)
-                x[t] = v[b * R + t];
+                x[t] = pk::from(v[b * R + t]);
             if constexpr(NS > 1)
             {
                 const int jm = j & (NS - 1);
                 constexpr int STEP = M / (NS * R);
 #pragma unroll
                 for(int t = 1; t < R; ++t)
-                    x[t] = cmul(x[t], __ldg(&tw[jm * t * STEP]));
+                    x[t] = pk::cmul(x[t], pk::from(__ldg(&tw[jm * t * STEP])));
             }
-            dft_bitrev<R>(x);
+            pk::dft_bitrev<R>(x);
             const int base = (j / NS) * (NS * R) + (j & (NS - 1));
 #pragma unroll
             for(int t = 0; t < R; ++t)
-                buf[phys(base + t * NS)] = x[bitrev<R>(t)];
+                buf[phys(base + t * NS)] = pk::to_float2(x[bitrev<R>(t)]);
         }
     }
 };
@@ -608,15 +621,12 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
             for(int i = 0; i < P; ++i)
             {
                 const int k = tid + i * TN;
-                const float2 a = buf[phys(k)];
-                float2 b = buf[phys((M - k) & (M - 1))];
-                b.y = -b.y;
-                const float2 sum = cadd(a, b);
-                const float2 dif = csub(a, b);
-                const float2 o = make_float2(dif.y, -dif.x); // -i (a - b)
-                const float2 w = __ldg(p.tw_post + k);
-                const float2 y = cadd(sum, cmul(o, w));
-                float mag = sqrtf(fmaf(y.x, y.x, y.y * y.y)) * p.coef_half;
+                const pk::c64 a = pk::from(buf[phys(k)]);
+                const pk::c64 b = pk::conj(pk::from(buf[phys((M - k) & (M - 1))]));
+                const pk::c64 o = pk::mul_neg_i(pk::sub(a, b)); // -i (a - b)
+                const pk::c64 y = pk::add(pk::add(a, b), pk::cmul(o, pk::from(__ldg(p.tw_post + k))));
+                const pk::c64 sq = pk::mul(y, y);
+                float mag = sqrt_mufu(pk::re(sq) + pk::im(sq)) * p.coef_half;
                 if(p.slope != nullptr)
                     mag *= __ldg(p.slope + k);
                 if(p.tsmooth)
@@ -675,7 +685,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
                         const int c = (CC == 2) ? d : 0;
                         in = proc[c] ? st[c][i] : prev_db[c * prev_slot_stride + k];
                     }
-                    outv = dbfs(in, p.db_min);
+                    outv = dbfs_mufu(in, p.db_min);
                     if(k >= 1)
                     {
                         if(p.normalize)
