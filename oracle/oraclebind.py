@@ -38,6 +38,12 @@ class WfoConfig(C.Structure):
     ]
 
 
+class WfoMeterConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("capture_channels", C.c_int32), ("meter_ms", C.c_int32),
+                ("rms_mode", C.c_int32), ("tsmoothing", C.c_int32), ("gravity", C.c_float),
+                ("fast_peaks", C.c_int32), ("floor_db", C.c_int32)]
+
+
 _lib = None
 
 
@@ -83,6 +89,12 @@ def lib():
                                   f32p, f32p]
     L.wfo_render_pixels.argtypes = [vp, f32p, f32p, f32p]
     L.wfo_r2c.argtypes = [f32p, C.c_int, f32p]
+    L.wfo_meter_window.argtypes = [C.POINTER(WfoMeterConfig)]
+    L.wfo_meter_create.restype = vp
+    L.wfo_meter_create.argtypes = [C.POINTER(WfoMeterConfig)]
+    L.wfo_meter_destroy.argtypes = [vp]
+    L.wfo_meter_reset.argtypes = [vp]
+    L.wfo_meter_run.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte), f32p]
     _lib = L
     return L
 
@@ -295,3 +307,51 @@ def r2c(x: np.ndarray) -> np.ndarray:
     out = np.zeros(2 * (n // 2 + 1), dtype=np.float32)
     lib().wfo_r2c(_fp(x), n, _fp(out))
     return out.view(np.complex64)
+
+
+def meter_config_from_settings(settings: dict | None = None, sample_rate=48000, channels=2) -> WfoMeterConfig:
+    """Reference setting keys (src/settings.hpp) -> the level meter's POD config (defaults: src/source.cpp:119-174)."""
+    s = dict(settings or {})
+    c = WfoMeterConfig()
+    c.sample_rate = sample_rate
+    c.capture_channels = min(channels, 2)
+    c.meter_ms = int(s.get("meter_buf", 150))
+    c.rms_mode = int(bool(s.get("rms_mode", True)))
+    c.tsmoothing = TSMOOTH.get(s.get("temporal_smoothing", "exp_moving_avg"), 0)
+    c.gravity = float(s.get("gravity", 0.65))
+    c.fast_peaks = int(bool(s.get("fast_peaks", False)))
+    c.floor_db = int(s.get("floor", -65))
+    return c
+
+
+class OracleMeter:
+    """Level meter (tick_meter) and RMS feed (update_input_rms) restated; see wf_oracle_meter.c."""
+
+    def __init__(self, settings: dict | None = None, sample_rate=48000, channels=2):
+        self.L = lib()
+        self.cfg = meter_config_from_settings(settings, sample_rate, channels)
+        self.h = self.L.wfo_meter_create(C.byref(self.cfg))
+        self.window = int(self.L.wfo_meter_window(C.byref(self.cfg)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wfo_meter_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        self.L.wfo_meter_reset(self.h)
+
+    def run(self, pcm: np.ndarray, n_ticks: int, hop: int, seconds: float = 1.0 / 60.0, meter=True, rms=False):
+        pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)
+        cc = self.cfg.capture_channels
+        assert pcm.shape[0] >= cc and pcm.shape[1] >= n_ticks * hop
+        db = np.zeros((n_ticks, cc), np.float32) if meter else None
+        lin = np.zeros((n_ticks, cc), np.float32) if meter else None
+        sil = np.zeros(n_ticks, np.uint8) if meter else None
+        r = np.zeros(n_ticks, np.float32) if rms else None
+        self.L.wfo_meter_run(self.h, _fp(pcm[0]), _fp(pcm[1]) if cc > 1 else None, n_ticks, hop, seconds, _fp(db), _fp(lin),
+                             None if sil is None else sil.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(r))
+        return {"db": db, "lin": lin, "silent": sil, "rms": r}

@@ -55,6 +55,8 @@ struct ProbeAPI {
     virtual void force_input_rms(bool enable, float v) = 0;
     virtual float gravity_for(float seconds) = 0;
     virtual float db_min() = 0;
+    virtual float meter_val(int ch) = 0;
+    virtual float meter_buf(int ch) = 0;
 };
 
 template<class Base>
@@ -103,6 +105,8 @@ public:
     }
     float gravity_for(float seconds) override { return this->get_gravity(seconds); }
     float db_min() override { return WAVSource::DB_MIN; }
+    float meter_val(int ch) override { return this->m_meter_val[ch]; }
+    float meter_buf(int ch) override { return this->m_meter_buf[ch]; }
 };
 
 struct Ref {
@@ -430,6 +434,38 @@ int wfref_run_stft(void *h, const float *pcm0, const float *pcm1, int64_t n_samp
         ++done;
     }
     return done;
+}
+
+// Level meter / RMS feed through the reference's own capture/tick loop: tick t is preceded by a push of samples
+// [t*hop, (t+1)*hop) stamped "now" (get_audio_sync()==0, so tick_meter consumes everything captured).
+//   meter mode (display_mode = level_meter / stepped_meter): out_db [n_ticks][capture_channels] = m_meter_val,
+//   out_lin = m_meter_buf, out_silent = m_last_silent            (src/source_generic.cpp:182-270)
+//   spectrum mode with normalize_volume: out_rms [n_ticks] = m_input_rms after the tick's update_input_rms()
+//                                                                 (src/source.cpp:1330-1331, 1842-1871)
+int wfref_run_meter(void *h, const float *pcm0, const float *pcm1, int n_ticks, int hop, float seconds, float *out_db,
+                    float *out_lin, unsigned char *out_silent, float *out_rms)
+{
+    auto r = static_cast<Ref *>(h);
+    auto p = r->probe.get();
+    const int cc = (int)p->capture_channels();
+    for(int t = 0; t < n_ticks; ++t)
+    {
+        r->clock_ns += audio_frames_to_ns(r->sample_rate, (uint64_t)hop);
+        wfref_push_audio(h, pcm0 + (size_t)t * hop, pcm1 ? pcm1 + (size_t)t * hop : nullptr, (uint32_t)hop, 0);
+        wfref_tick(h, seconds);
+        for(int c = 0; c < cc; ++c)
+        {
+            if(out_db)
+                out_db[t * cc + c] = p->meter_val(c);
+            if(out_lin)
+                out_lin[t * cc + c] = p->meter_buf(c);
+        }
+        if(out_silent)
+            out_silent[t] = p->last_silent() ? 1 : 0;
+        if(out_rms)
+            out_rms[t] = p->input_rms();
+    }
+    return n_ticks;
 }
 
 } // extern "C"

@@ -76,6 +76,7 @@ def lib():
     L.wfref_get_render_buf.argtypes = [vp, C.c_int, f32p]
     L.wfref_run_stft.argtypes = [vp, f32p, f32p, C.c_int64, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p,
                                  C.c_int, C.POINTER(C.c_ubyte)]
+    L.wfref_run_meter.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte), f32p]
     _lib = L
     return L
 
@@ -276,3 +277,20 @@ class RefSource:
         done = self.L.wfref_run_stft(self.h, _fp(ch0), _fp(ch1), pcm.shape[1], T, hop, seconds, _fp(rms), _fp(db),
                                      _fp(pts), int(fma3), silent.ctypes.data_as(C.POINTER(C.c_ubyte)))
         return {"frames": done, "db": db, "points": pts, "silent": silent}
+
+    def run_meter(self, pcm: np.ndarray, n_ticks: int, hop: int, seconds: float = 1.0 / 60.0):
+        """Level-meter ticks (display_mode level_meter/stepped_meter) or, with normalize_volume on in a spectrum
+        mode, the per-tick m_input_rms.  pcm: [capture_channels, >= n_ticks*hop].
+        Returns dict(db=[T,cc] m_meter_val, lin=[T,cc] m_meter_buf, silent=[T], rms=[T] m_input_rms)."""
+        pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)
+        assert pcm.shape[1] >= n_ticks * hop
+        ch0 = pcm[0]
+        ch1 = pcm[1] if pcm.shape[0] > 1 else None
+        cc = self.capture_channels
+        db = np.zeros((n_ticks, cc), dtype=np.float32)
+        lin = np.zeros((n_ticks, cc), dtype=np.float32)
+        silent = np.zeros(n_ticks, dtype=np.uint8)
+        rms = np.zeros(n_ticks, dtype=np.float32)
+        self.L.wfref_run_meter(self.h, _fp(ch0), _fp(ch1), n_ticks, hop, seconds, _fp(db), _fp(lin),
+                               silent.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(rms))
+        return {"db": db, "lin": lin, "silent": silent, "rms": rms}

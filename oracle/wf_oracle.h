@@ -110,6 +110,31 @@ int wfo_run_stft_px(wfo_source *s, const float *pcm0, const float *pcm1, int n_f
  * deps/fftw-3.3.11/doc/reference.texi:1926-1936, api/plan-dft-r2c-1d.c:23-26. Any N >= 2. */
 void wfo_r2c(const float *in, int n, float *out_interleaved);
 
+/* ---- level meter + RMS feed (wf_oracle_meter.c): src/source_generic.cpp:182-270, :392-403, src/source.cpp:810-836,
+ *      :1105-1128, :1842-1871 ------------------------------------------------------------------------------------ */
+typedef struct wfo_meter_config {
+    uint32_t sample_rate;
+    int32_t capture_channels; /* 1 or 2 */
+    int32_t meter_ms;         /* m_meter_ms: ring length = (sample_rate * ms / 1000) & -16 */
+    int32_t rms_mode;         /* m_meter_rms: 1 = RMS, 0 = peak */
+    int32_t tsmoothing;
+    float gravity;
+    int32_t fast_peaks;
+    int32_t floor_db;
+} wfo_meter_config;
+typedef struct wfo_meter wfo_meter;
+int wfo_meter_window(const wfo_meter_config *cfg);
+wfo_meter *wfo_meter_create(const wfo_meter_config *cfg);
+void wfo_meter_destroy(wfo_meter *m);
+void wfo_meter_reset(wfo_meter *m); /* capture-timeout branch, src/source_generic.cpp:184-199 */
+void wfo_meter_tick(wfo_meter *m, const float *const x[2], size_t n, float seconds);
+float wfo_meter_feed_rms(wfo_meter *m, const float *const x[2], size_t n); /* -> m_input_rms */
+float wfo_meter_val(const wfo_meter *m, int c);
+float wfo_meter_buf(const wfo_meter *m, int c);
+int wfo_meter_last_silent(const wfo_meter *m);
+void wfo_meter_run(wfo_meter *m, const float *pcm0, const float *pcm1, int n_ticks, int hop, float seconds,
+                   float *out_db, float *out_lin, unsigned char *out_silent, float *out_rms);
+
 #ifdef __cplusplus
 }
 #endif

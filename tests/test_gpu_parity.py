@@ -322,3 +322,73 @@ def test_display_stage_pixels(settings, channels):
     same = out["min"][..., 1] == exp_min[..., 1]
     assert same.mean() > 0.9  # an exact tie between two points can flip under a 1e-5 px difference
     assert check_points(settings, channels, out["db"], out["points"]) < 2e-6
+
+
+# ---- the cluster ("wide") kernel: R CTAs per stream working on R ticks at once (csrc/wf_wide.cuh) ----------------
+
+WIDE_CASES = [
+    # (settings, channels, hop_div, T) — T not a multiple of R, stereo, mono-mix, display stages, gate-heavy
+    ({"fft_size": 4096, "window": "blackman_harris", "channel_mode": "stereo"}, 2, 4, 13),
+    ({"fft_size": 8192, "window": "hann", "interp_mode": "lanczos", "filter_mode": "gauss"}, 1, 4, 11),
+    ({"fft_size": 16384, "window": "hann", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0, "fast_peaks": True}, 2, 2, 9),
+    ({"fft_size": 4096, "display_mode": "bars", "interp_mode": "catmull_rom", "mirror_freq_axis": True}, 2, 2, 10),
+    ({"fft_size": 32768, "window": "hann"}, 1, 2, 5),
+]
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("settings,channels,hop_div,T", WIDE_CASES)
+def test_wide_kernel_is_bit_identical_to_one_group_kernel(settings, channels, hop_div, T, R, monkeypatch):
+    """Distributing a stream's bins over a cluster must not change a single bit: the recurrences are only
+    distributed, never reassociated.  Also checks both against the oracle."""
+    import torch
+    from waveform_b200 import Engine
+
+    S = 3
+    monkeypatch.setenv("WF_WIDE_R", "1")
+    e1 = Engine(settings, channels=channels, max_streams=S)
+    monkeypatch.setenv("WF_WIDE_R", str(R))
+    e2 = Engine(settings, channels=channels, max_streams=S)
+    N = e1.fft_size
+    hop = N // hop_div
+    cc = e1.capture_channels
+    pcm = synth_pcm(S, cc, (T - 1) * hop + N, zero_frames=[(1, 2, 6)], frame_len=N, hop=hop)
+    x = torch.from_numpy(pcm).cuda()
+    a = e1.process(x, T, hop, want_points=True, want_peak=True)
+    b = e2.process(x, T, hop, want_points=True, want_peak=True)
+    torch.cuda.synchronize()
+    for key in ("db", "points", "silent", "peak"):
+        assert np.array_equal(a[key].cpu().numpy(), b[key].cpu().numpy()), key
+    sa, sb = e1.get_state(), e2.get_state()
+    for key in ("tsmooth", "hold_db", "flags"):
+        assert np.array_equal(sa[key], sb[key]), key
+    ref_db, _, ref_sil = _oracle_batch(settings, channels, pcm, T, hop)
+    rep = parity_report(b["db"].cpu().numpy(), ref_db, db_min=e2.db_min)
+    assert rep["ok"] and rep["normwise"] < 1e-6, rep
+    assert np.array_equal(b["silent"].cpu().numpy(), ref_sil)
+
+
+@pytest.mark.parametrize("R", [2, 8])
+def test_wide_kernel_gate_hold_and_wakeup(R, monkeypatch):
+    """Silence inside a round of R ticks: decay, freeze below floor-10 dB, wake-up — the lazily evaluated cluster-wide
+    reduction must flip m_last_silent on the same tick as the reference (src/source_generic.cpp:63-95)."""
+    monkeypatch.setenv("WF_WIDE_R", str(R))
+    settings = {"fft_size": 4096, "window": "hann", "gravity": 0.3, "floor": -40, "channel_mode": "stereo"}
+    S, T, N = 3, 37, 4096
+    pcm = synth_pcm(S, 2, T * N)
+    pcm[:, :, 3 * N:] = 0.0
+    pcm[1, 1, 5 * N: 9 * N] = 0.05   # one channel keeps playing for a while
+    pcm[2, :, 29 * N: 31 * N] = 0.1  # wakes up again
+    eng = _engine(settings, 2, S)
+    out = eng.process(pcm, T, N)
+    ref_db, _, ref_sil = _oracle_batch(settings, 2, pcm, T, N)
+    assert ref_sil.sum() > 0, "test must exercise the gate"
+    assert np.array_equal(out["silent"], ref_sil)
+    rep = parity_report(out["db"], ref_db, db_min=eng.db_min)
+    assert rep["ok"], rep
+    # state carries over a call boundary that falls inside the silent stretch
+    eng2 = _engine(settings, 2, S)
+    a = eng2.process(pcm[:, :, : 6 * N], 6, N)
+    b = eng2.process(pcm[:, :, 6 * N:], T - 6, N)
+    assert np.array_equal(np.concatenate([a["db"], b["db"]], axis=1), out["db"])
+    assert np.array_equal(np.concatenate([a["silent"], b["silent"]], axis=1), out["silent"])

@@ -15,11 +15,19 @@ SHAPES = [
     ("c4 N=8192 hop 2048, 800-pt Lanczos curve", {"fft_size": 8192, "window": "hann", "interp_mode": "lanczos"}, 1, 256, 256, 2048, "points"),
     ("c4' N=8192 hop 2048, bins out", {"fft_size": 8192, "window": "hann"}, 1, 256, 256, 2048, "db"),
     ("c5 N=16384 hop N, peak", {"fft_size": 16384, "window": "hann"}, 1, 128, 64, 16384, "db+peak"),
+    ("c5 full N=16384 128x256", {"fft_size": 16384, "window": "hann"}, 1, 128, 256, 16384, "db+peak"),
+    ("N=4096 mono 4096x16 hop N", {"fft_size": 4096, "window": "hann"}, 1, 4096, 16, 4096, "db"),
+    ("N=8192 mono 2048x16 hop N", {"fft_size": 8192, "window": "hann"}, 1, 2048, 16, 8192, "db"),
     ("c1 N=1024 bars catrom", {"fft_size": 1024, "window": "hann", "display_mode": "bars", "interp_mode": "catmull_rom"}, 1, 4096, 16, 1024, "points"),
     ("N=2048 generic (WF_FORCE_GENERIC)", {"fft_size": 2048, "window": "hann"}, 1, 4096, 16, 2048, "db"),
 ]
+import os
+ONLY = [a.split("=",1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
+ITERS = int(([a.split("=",1)[1] for a in sys.argv[1:] if a.startswith("--iters=")] or ["10"])[0])
+if ONLY:
+    SHAPES = [x for x in SHAPES if any(o in x[0] for o in ONLY)]
+print("env:", {k: v for k, v in os.environ.items() if k.startswith("WF_")})
 for name, settings, ch, S, T, hop, mode in SHAPES:
-    import os
     if "FORCE_GENERIC" in name:
         os.environ["WF_FORCE_GENERIC"] = "1"
     eng = Engine(settings, channels=ch, max_streams=S)
@@ -38,7 +46,7 @@ for name, settings, ch, S, T, hop, mode in SHAPES:
     for _ in range(3): step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    K = 10
+    K = ITERS
     e0.record(st)
     for _ in range(K): step()
     e1.record(st); torch.cuda.synchronize()

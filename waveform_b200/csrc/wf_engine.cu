@@ -19,6 +19,7 @@
 #include "wf_kernels.cuh"
 #include "wf_fast2048.cuh"
 #include "wf_anyn.cuh"
+#include "wf_wide.hpp"
 #ifdef WF_BUILD_EXPERIMENTAL
 #include "experimental/wf_fast2048b.cuh"
 #endif
@@ -40,6 +41,7 @@ struct wf_engine {
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
     bool use_pdl = true;        // WF_NO_PDL=1: launch the fast kernel without programmatic dependent launch
+    int wide_r = 0;             // WF_WIDE_R=1|2|4|8: force the cluster size of the wide kernel (1 = never use it); 0 = automatic
     char fast_kernel = 'a';     // WF_FAST_KERNEL=b selects csrc/experimental/wf_fast2048b.cuh when built with -DWF_BUILD_EXPERIMENTAL
 
     // device tables
@@ -201,9 +203,36 @@ int launch_fused(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra_
     return WF_OK;
 }
 
+// Cluster size of the wide kernel (wf_wide.cuh) for this launch, 1 = use the one-group-per-stream kernel.
+// The wide kernel pays off when there are too few streams to fill the GPU: R CTAs per stream work on R ticks at once.
+int pick_wide_r(const wf_engine *e, const KParams &kp, bool display)
+{
+    const int N = e->tab.N;
+    if(!wide_supported(N) || e->wide_r == 1)
+        return 1;
+    if(wide_smem_bytes(N, kp.dch, kp.n_points, display) > 227 * 1024)
+        return 1;
+    if(e->wide_r == 2 || e->wide_r == 4 || e->wide_r == 8)
+        return e->wide_r;
+    int r = 1;
+    while(r < 8 && (long long)kp.n_streams * r < 2LL * e->sm_count && 2 * r <= kp.n_frames)
+        r *= 2;
+    return r;
+}
+
 template<int CC>
 int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
 {
+    {
+        const bool display = kp.out_points || kp.out_pixels || kp.out_min;
+        const int R = pick_wide_r(e, kp, display);
+        if(R > 1)
+        {
+            WF_CUDA(e, wide_launch(e->tab.N, CC, R, kp, st, display, e->device));
+            e->launches++;
+            return WF_OK;
+        }
+    }
     switch(e->tab.N)
     {
     case 128: return launch_fused<128, CC>(e, kp, st, extra);
@@ -520,6 +549,9 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->fast_kernel = fk[0];
         const char *np = getenv("WF_NO_PDL");
         e->use_pdl = !(np && np[0] == '1');
+        const char *wr = getenv("WF_WIDE_R");
+        if(wr)
+            e->wide_r = atoi(wr);
         const char *wo = getenv("WF_FAST_WPC");
         if(wo)
             e->fast_wpc_override = atoi(wo);

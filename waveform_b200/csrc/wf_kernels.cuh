@@ -103,6 +103,12 @@ struct Geo {
     static constexpr int CTA = (TN >= 128) ? TN : 128;        // threads per CTA
     static constexpr int GROUPS = CTA / TN;                   // streams per CTA
     static constexpr int BUF = M + (M >> 5);                  // padded exchange buffer, float2 elements
+    // register cap: 128 registers/thread (512 threads per SM resident) — without it ptxas takes ~250 registers for
+    // hoisted twiddle loads and the kernels run at 8 warps/SM
+#ifndef WF_THREADS_PER_SM
+#define WF_THREADS_PER_SM 512
+#endif
+    static constexpr int MINB = (WF_THREADS_PER_SM / CTA) > 0 ? (WF_THREADS_PER_SM / CTA) : 1;
 };
 
 __device__ __forceinline__ int phys(int i) { return i + (i >> 5); }
@@ -292,10 +298,10 @@ struct Fft<N, PlanT<TN_, R0, Rest...>> {
     static constexpr int P = M / TN;
     using P0 = Pass<M, TN, R0, 1, true>;
 
-    // Loads the frame (as M complex points), applies the window, reports whether any sample is nonzero.
-    static __device__ __forceinline__ bool load_frame(float2 (&v)[P], const float *frame, const KParams &p, int tid)
+    // Issues the loads of one frame (as M complex points) into registers; no use of the values yet, so the loads
+    // stay in flight across whatever the caller does next (software prefetch of the next tick).
+    static __device__ __forceinline__ void load_raw(float2 (&v)[P], const float *frame, const KParams &p, int tid)
     {
-        bool nz = false;
         if(p.aligned8)
         {
             const float2 *f2 = reinterpret_cast<const float2 *>(frame);
@@ -316,6 +322,11 @@ struct Fft<N, PlanT<TN_, R0, Rest...>> {
                     v[b * R0 + t] = make_float2(ldg_stream_f1(frame + 2 * n), ldg_stream_f1(frame + 2 * n + 1));
                 }
         }
+    }
+    // Non-zero test (src/source_generic.cpp:63-76) and window multiply (:97-103) on a loaded frame.
+    static __device__ __forceinline__ bool finish_load(float2 (&v)[P], const KParams &p, int tid)
+    {
+        bool nz = false;
 #pragma unroll
         for(int i = 0; i < P; ++i)
             nz |= (v[i].x != 0.0f) | (v[i].y != 0.0f);
@@ -332,6 +343,19 @@ struct Fft<N, PlanT<TN_, R0, Rest...>> {
                 }
         }
         return nz;
+    }
+    // Pulls a frame's cache lines into L2 (for plans whose register budget has no room for a register prefetch).
+    static __device__ __forceinline__ void prefetch_l2(const float *frame, int tid)
+    {
+        constexpr int LINES = (N * 4) / 128;
+        for(int l = tid; l < LINES; l += TN)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(frame + l * 32));
+    }
+    // Loads the frame (as M complex points), applies the window, reports whether any sample is nonzero.
+    static __device__ __forceinline__ bool load_frame(float2 (&v)[P], const float *frame, const KParams &p, int tid)
+    {
+        load_raw(v, frame, p, tid);
+        return finish_load(v, p, tid);
     }
 
     // Complex FFT of the M points in v; result X[k] (natural order) is left in buf[phys(k)].
@@ -525,7 +549,7 @@ __device__ __forceinline__ void display_stage(const KParams &p, const float *dbs
 
 // ---- the fused kernel ------------------------------------------------------------------------------
 template<int N, int CC>
-__global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_constant__ KParams p)
+__global__ void __launch_bounds__(Geo<N>::CTA, Geo<N>::MINB) stft_fused_kernel(const __grid_constant__ KParams p)
 {
     using G = Geo<N>;
     using F = Fft<N, typename Plan<N>::type>;
@@ -565,6 +589,13 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
     const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
     float *hold_s = p.hold_db + (size_t)s * och * B;
 
+    // Software pipelining of the PCM loads: plans with <= 16 points per thread keep the NEXT frame's samples in
+    // registers across the epilogue; the others (no register room) pull the next frame into L2.
+    constexpr bool REGPF = (P <= 16);
+    float2 v[P];
+    if(REGPF && p.n_frames > 0)
+        F::load_raw(v, pcm_s, p, tid);
+
     for(int t = 0; t < p.n_frames; ++t)
     {
         const bool skip_all = (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * p.n_frames + t] != 0);
@@ -579,10 +610,23 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
 #pragma unroll
         for(int c = 0; c < CC; ++c)
         {
-            float2 v[P];
             const float *frame = pcm_s + (size_t)c * p.channel_stride + (size_t)t * p.hop;
-            const bool nz = group_any<TN>(F::load_frame(v, frame, p, tid));
+            if(!REGPF)
+                F::load_raw(v, frame, p, tid);
+            const bool nz = group_any<TN>(F::finish_load(v, p, tid));
             F::run(v, buf, p.tw, tid);
+            {
+                // next frame of this stream: the other channel of this tick, or channel 0 of the next tick
+                const float *next = (c + 1 < CC) ? frame + p.channel_stride
+                                                 : pcm_s + (size_t)(t + 1) * p.hop;
+                if(c + 1 < CC || t + 1 < p.n_frames)
+                {
+                    if(REGPF)
+                        F::load_raw(v, next, p, tid);
+                    else
+                        F::prefetch_l2(next, tid);
+                }
+            }
 
             // ---- gate, src/source_generic.cpp:63-95 ----
             bool do_proc = !skip_all;
@@ -765,7 +809,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA) stft_fused_kernel(const __grid_co
 }
 
 // peak normalisation pass: out[row][k] += gain[t] for k >= 1 (row = (stream, frame, channel))
-__global__ void peak_normalize_kernel(float *data, int n_streams, int n_frames, int rows_per_frame, int row_len,
+static __global__ void peak_normalize_kernel(float *data, int n_streams, int n_frames, int rows_per_frame, int row_len,
                                       const float *peak, float target_db, float max_gain)
 {
     const long long rows = (long long)n_streams * n_frames * rows_per_frame;
@@ -779,7 +823,7 @@ __global__ void peak_normalize_kernel(float *data, int n_streams, int n_frames, 
     }
 }
 
-__global__ void fill_kernel(float *p, long long n, float v)
+static __global__ void fill_kernel(float *p, long long n, float v)
 {
     for(long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         p[i] = v;

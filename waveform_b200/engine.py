@@ -13,12 +13,14 @@ caller (or a test) configures the engine exactly as it would configure the OBS s
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libwfstft.so"
+# WF_LIB_PATH: development knob to A/B a differently compiled build of the SAME library (never a fallback)
+LIB_PATH = Path(os.environ["WF_LIB_PATH"]) if os.environ.get("WF_LIB_PATH") else _HERE / "lib" / "libwfstft.so"
 
 WF_OK = 0
 WF_ERR_INVALID_ARG = -1
