@@ -210,6 +210,66 @@ int64_t wf_launch_count(const wf_engine *e);
  * measured with CUDA events on the launching stream; < 0 if none. Synchronises on the recorded events. */
 float wf_last_kernel_ms(wf_engine *e);
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Level meter and RMS feed — the other reductions behind the same backend seam:
+ *   WAVSource::tick_meter            src/source.hpp:276, src/source_generic.cpp:182-270, src/source_avx.cpp:202-301
+ *   WAVSource::update_input_rms      src/source.hpp:277, src/source_generic.cpp:392-403, src/source_avx.cpp:303-322
+ *   the ring that feeds it           src/source.cpp:810-836 (sync_rms_buffer), :1842-1871 (capture_audio)
+ *   meter setup                      src/source.cpp:1105-1128
+ * A wf_meter keeps, per stream, the ring of the last `window` samples (m_decibels repurposed, :205-222), the EMA value
+ * m_meter_buf and m_last_silent.  One call = n_streams sources x n_ticks ticks; tick t consumes samples
+ * [t*hop, (t+1)*hop) of each capture channel (everything captured since the previous tick).
+ * Peak values are bit-exact; RMS values are summed in blocks (not in ring order) and agree to ~1e-6 relative. */
+typedef enum { WF_METER_PEAK = 0, WF_METER_RMS = 1, WF_METER_INPUT_RMS = 2 } wf_meter_mode;
+
+typedef struct wf_meter_config {
+    uint32_t struct_size;     /* = sizeof(wf_meter_config) */
+    int32_t device;           /* CUDA device ordinal, -1 = current */
+    int32_t max_streams;
+    uint32_t sample_rate;     /* m_audio_info.samples_per_sec */
+    int32_t capture_channels; /* 1 or 2 */
+    int32_t mode;             /* wf_meter_mode: PEAK / RMS = m_meter_rms false / true; INPUT_RMS = the volume-normalisation
+                                 feed: sqrt(mean over the last (sample_rate & -16) samples of (max over channels |x|)^2) */
+    int32_t meter_ms;         /* m_meter_ms: window = (sample_rate * meter_ms / 1000) & -16 (ignored for INPUT_RMS) */
+    int32_t tsmoothing;       /* wf_tsmooth */
+    float gravity;            /* m_gravity */
+    int32_t fast_peaks;       /* m_fast_peaks */
+    int32_t floor_db;         /* m_floor: a channel below floor-10 dB counts as silent */
+} wf_meter_config;
+
+typedef struct wf_meter_batch {
+    uint32_t struct_size;     /* = sizeof(wf_meter_batch) */
+    int32_t n_streams;
+    int32_t n_ticks;
+    int32_t hop;              /* new samples per tick (>= 1) */
+    int32_t first_stream;
+    float seconds;            /* tick delta for TVEXPONENTIAL gravity */
+    const float *pcm;         /* planar float PCM, host or device: sample i of channel c of stream s at
+                                 pcm[s*stream_stride + c*channel_stride + i], i < n_ticks*hop */
+    int64_t stream_stride;
+    int64_t channel_stride;
+    float *out_db;            /* optional [n_streams][n_ticks][capture_channels] m_meter_val (dBFS); unused for INPUT_RMS */
+    float *out_lin;           /* optional [n_streams][n_ticks][capture_channels] m_meter_buf;
+                                 INPUT_RMS: [n_streams][n_ticks] m_input_rms (feed it to wf_batch.input_rms) */
+    uint8_t *out_silent;      /* optional [n_streams][n_ticks] m_last_silent after the tick; unused for INPUT_RMS */
+} wf_meter_batch;
+
+typedef struct wf_meter wf_meter;
+
+void wf_meter_config_init(wf_meter_config *cfg); /* plugin defaults: 150 ms, RMS, EMA 0.65, floor -65 (src/source.cpp:119-174) */
+int wf_meter_create(const wf_meter_config *cfg, wf_meter **out); /* ≙ WAVSource::update in meter mode */
+void wf_meter_destroy(wf_meter *m);
+const char *wf_meter_last_error(const wf_meter *m);
+int32_t wf_meter_window(const wf_meter *m); /* ring length in samples (m_fft_size in meter mode / m_input_rms_size) */
+int wf_meter_process(wf_meter *m, const wf_meter_batch *batch);
+int wf_meter_process_async(wf_meter *m, const wf_meter_batch *batch, void *cuda_stream);
+/* ≙ the capture-timeout branch of tick_meter (src/source_generic.cpp:184-199): unless already silent, zero the ring,
+ * m_meter_buf := 0, m_meter_val := DB_MIN, m_last_silent := true. */
+int wf_meter_reset(wf_meter *m, int32_t first_stream, int32_t count);
+int64_t wf_meter_launch_count(const wf_meter *m);
+float wf_meter_last_kernel_ms(wf_meter *m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,8 +127,10 @@ void wfo_meter_tick(wfo_meter *m, const float *const x[2], size_t n, float secon
 {
     const int cc = m->cfg.capture_channels;
     const int W = m->W;
+    /* capture_audio keeps at most m_fft_size pending samples per channel (src/source.cpp:1881-1884) */
+    const size_t skip = (n > (size_t)W) ? n - (size_t)W : 0;
     for(int c = 0; c < cc; ++c)
-        ring_push(m->ring[c], W, &m->pos[c], x[c], n);
+        ring_push(m->ring[c], W, &m->pos[c], x[c] + skip, n - skip);
     for(int c = 0; c < cc; ++c)
     {
         float out = 0.0f;

@@ -82,5 +82,35 @@ def main():
         print(name, "N", N, "db", r["db"].shape, "points", r["points"].shape, "silent ticks", int(r["silent"].sum()))
 
 
+# Level meter / RMS feed fixtures: what the unmodified reference's tick_meter /
+# update_input_rms produce tick by tick (src/source_generic.cpp:182-270, :392-403).
+METER_CASES = {
+    "rms_150ms_stereo": dict(kind="meter", settings={"meter_buf": 150, "rms_mode": True}, channels=2, T=50, hop=800),
+    "peak_fast_100ms": dict(kind="meter", settings={"meter_buf": 100, "rms_mode": False, "fast_peaks": True}, channels=2,
+                            T=50, hop=800),
+    "rms_20ms_mono_nosmooth": dict(kind="meter", settings={"meter_buf": 20, "rms_mode": True, "temporal_smoothing": "none"},
+                                   channels=1, T=64, hop=441),
+    "rms_feed_stereo": dict(kind="rms_feed", settings={}, channels=2, T=75, hop=800),
+}
+
+
+def main_meter():
+    for name, c in METER_CASES.items():
+        T, hop, ch = c["T"], c["hop"], c["channels"]
+        pcm = synth_pcm(1, ch, T * hop, seed=0xB200 + len(name))[0]
+        pcm[:, (T // 2) * hop: (3 * T // 4) * hop] = 0.0
+        if c["kind"] == "meter":
+            ref = RefSource({"display_mode": "level_meter", **c["settings"]}, impl=IMPL_GENERIC, channels=ch)
+        else:
+            ref = RefSource({"normalize_volume": True, "fft_size": 1024}, impl=IMPL_GENERIC, channels=ch)
+        r = ref.run_meter(pcm, T, hop)
+        np.savez_compressed(OUT / f"meter_{name}.npz", kind=c["kind"], settings=json.dumps(c["settings"]), channels=ch,
+                            hop=hop, n_ticks=T, pcm=pcm, db=r["db"], lin=r["lin"], silent=r["silent"], rms=r["rms"])
+        print("meter", name, "window", ref.fft_size, "silent ticks", int(r["silent"].sum()), "rms[-1]", float(r["rms"][-1]))
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--meter-only" not in sys.argv:
+        main()
+    main_meter()

@@ -336,15 +336,19 @@ WIDE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("v3", ["1", "0"])
 @pytest.mark.parametrize("R", [2, 4, 8])
 @pytest.mark.parametrize("settings,channels,hop_div,T", WIDE_CASES)
-def test_wide_kernel_is_bit_identical_to_one_group_kernel(settings, channels, hop_div, T, R, monkeypatch):
+def test_wide_kernel_is_bit_identical_to_one_group_kernel(settings, channels, hop_div, T, R, v3, monkeypatch):
     """Distributing a stream's bins over a cluster must not change a single bit: the recurrences are only
-    distributed, never reassociated.  Also checks both against the oracle."""
+    distributed, never reassociated.  Also checks both against the oracle.  v3 = "1": the CTA-per-tick kernel
+    (csrc/wf_v3.cuh, cluster size 1 vs R; 16384 has no size-1 variant, so 2 vs R); "0": the first-generation pair
+    (wf_kernels.cuh vs wf_wide.cuh)."""
     import torch
     from waveform_b200 import Engine
 
     S = 3
+    monkeypatch.setenv("WF_V3", v3)
     monkeypatch.setenv("WF_WIDE_R", "1")
     e1 = Engine(settings, channels=channels, max_streams=S)
     monkeypatch.setenv("WF_WIDE_R", str(R))
@@ -368,10 +372,12 @@ def test_wide_kernel_is_bit_identical_to_one_group_kernel(settings, channels, ho
     assert np.array_equal(b["silent"].cpu().numpy(), ref_sil)
 
 
-@pytest.mark.parametrize("R", [2, 8])
-def test_wide_kernel_gate_hold_and_wakeup(R, monkeypatch):
+@pytest.mark.parametrize("v3", ["1", "0"])
+@pytest.mark.parametrize("R", [1, 2, 8])
+def test_wide_kernel_gate_hold_and_wakeup(R, v3, monkeypatch):
     """Silence inside a round of R ticks: decay, freeze below floor-10 dB, wake-up — the lazily evaluated cluster-wide
     reduction must flip m_last_silent on the same tick as the reference (src/source_generic.cpp:63-95)."""
+    monkeypatch.setenv("WF_V3", v3)
     monkeypatch.setenv("WF_WIDE_R", str(R))
     settings = {"fft_size": 4096, "window": "hann", "gravity": 0.3, "floor": -40, "channel_mode": "stereo"}
     S, T, N = 3, 37, 4096

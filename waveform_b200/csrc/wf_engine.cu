@@ -20,6 +20,7 @@
 #include "wf_fast2048.cuh"
 #include "wf_anyn.cuh"
 #include "wf_wide.hpp"
+#include "wf_v3.hpp"
 #ifdef WF_BUILD_EXPERIMENTAL
 #include "experimental/wf_fast2048b.cuh"
 #endif
@@ -47,6 +48,8 @@ struct wf_engine {
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
     float *d_tw = nullptr, *d_tw_post = nullptr;
+    float *d_tw1 = nullptr, *d_tw2 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
+    bool use_v3 = true;                        // WF_V3=0: fall back to the first-generation kernels (A/B tests)
     float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
     int *d_band_widths = nullptr, *d_band_offsets = nullptr;
     // per-stream state
@@ -220,11 +223,31 @@ int pick_wide_r(const wf_engine *e, const KParams &kp, bool display)
     return r;
 }
 
+// Cluster size for the CTA-per-tick kernel (wf_v3.cuh): 1 when the streams alone fill the GPU, else up to 8 CTAs
+// (= 8 ticks in flight) per stream.
+int pick_v3_r(const wf_engine *e, const KParams &kp)
+{
+    const int rmin = v3_min_cluster(e->tab.N);
+    if(e->wide_r == 1 || e->wide_r == 2 || e->wide_r == 4 || e->wide_r == 8)
+        return std::max(rmin, e->wide_r);
+    int r = rmin;
+    while(r < 8 && (long long)kp.n_streams * r < 3LL * e->sm_count && 2 * r <= kp.n_frames)
+        r *= 2;
+    return r;
+}
+
 template<int CC>
 int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
 {
     {
         const bool display = kp.out_points || kp.out_pixels || kp.out_min;
+        if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.n_points, display) <= 227 * 1024)
+        {
+            const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+            WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, st, display, e->device));
+            e->launches++;
+            return WF_OK;
+        }
         const int R = pick_wide_r(e, kp, display);
         if(R > 1)
         {
@@ -552,6 +575,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *wr = getenv("WF_WIDE_R");
         if(wr)
             e->wide_r = atoi(wr);
+        const char *v3 = getenv("WF_V3");
+        e->use_v3 = !(v3 && v3[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
         if(wo)
             e->fast_wpc_override = atoi(wo);
@@ -590,6 +615,13 @@ int wf_create(const wf_config *cfg, wf_engine **out)
     WF_TRY(upload(e, &e->d_rolloff, t.rolloff));
     WF_TRY(upload(e, &e->d_tw, t.tw));
     WF_TRY(upload(e, &e->d_tw_post, t.tw_post));
+    if(v3_supported(t.N))
+    {
+        std::vector<float> tw1, tw2;
+        v3_build_twiddles(t.N, tw1, tw2);
+        WF_TRY(upload(e, &e->d_tw1, tw1));
+        WF_TRY(upload(e, &e->d_tw2, tw2));
+    }
     WF_TRY(upload(e, &e->d_interp_idx, t.interp_indices));
     WF_TRY(upload(e, &e->d_interp_w, t.interp_weights));
     WF_TRY(upload(e, &e->d_gauss, t.gauss));
@@ -617,7 +649,7 @@ void wf_destroy(wf_engine *e)
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
     }
-    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_interp_idx, e->d_interp_w,
+    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
                     e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min};
     for(void *p : ptrs)

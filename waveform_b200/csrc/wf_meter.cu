@@ -1,0 +1,627 @@
+// wf_meter.cu — level meter (tick_meter) and RMS feed (update_input_rms) of the plugin as batched sm_100a reductions
+// behind the C ABI of include/wfstft.h (wf_meter_*).  SURVEY.md §8(f) rank 4 / §8(a) row a9.
+//
+// Reference semantics restated (paths relative to the reference tree):
+//   tick_meter          src/source_generic.cpp:182-270: ring of the last W samples -> RMS or peak -> EMA -> dBFS -> silent
+//   update_input_rms    src/source_generic.cpp:392-403 + src/source.cpp:810-836,1842-1871: ring of the last RW values
+//                       (max over channels |x|)^2 -> sqrt(mean)
+//
+// HBM-bound integer/float streaming work, so the design is about touching each sample once:
+//   K1 block partials   every 256-sample block of the stream's timeline (history ring ++ new PCM) is reduced once
+//                       (sum of squares / max |x| / sum of (max_c |x_c|)^2), coalesced 128-byte warp loads;
+//   K2 window combine   one warp per (stream, tick, channel): whole blocks from the partials (L2-resident) + the two
+//                       ragged edges from the samples — O(W/256) instead of O(W) per tick, windows overlap W/hop times;
+//   K3 recurrence       one thread per stream walks the ticks: sqrt/mean, EMA (fast-peaks rule), dBFS, m_last_silent;
+//   K4 history          the last W samples become the ring for the next call (double-buffered).
+// There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "wf_tables.hpp"
+#include "wfstft.h"
+
+namespace {
+
+constexpr int kBL = 256; // samples per partial block
+
+struct MParams {
+    const float *pcm;
+    long long stream_stride, channel_stride;
+    const float *hist;   // [streams][cc][W] time-ordered ring contents before this call
+    float *hist_next;    // same layout, after this call
+    float *partial;      // [streams][pc][nblk]
+    float *raw;          // [streams][ticks][pc]
+    float *buf;          // [streams][2] m_meter_buf
+    unsigned char *flags;// [streams] m_last_silent
+    float *out_db, *out_lin;
+    unsigned char *out_silent;
+    int n_streams, n_ticks, hop, W, cc, pc, nblk, mode;
+    float g, g2;
+    int tsmooth, fast_peaks;
+    float floor_m10, db_min;
+};
+
+// sample u of the stream's timeline: history ring first, then this call's PCM
+__device__ __forceinline__ float vsample(const MParams &p, const float *hist_sc, const float *pcm_sc, long long u)
+{
+    return (u < p.W) ? hist_sc[u] : __ldg(pcm_sc + (u - p.W));
+}
+
+// the value one sample contributes to partial channel `c`
+__device__ __forceinline__ float contrib(const MParams &p, int s, int c, long long u)
+{
+    if(p.mode == WF_METER_INPUT_RMS)
+    {
+        // (max over channels |x|)^2, src/source.cpp:1852-1862
+        float val = 0.0f;
+        for(int ch = 0; ch < p.cc; ++ch)
+        {
+            const float x = vsample(p, p.hist + ((size_t)s * p.cc + ch) * p.W,
+                                    p.pcm + (size_t)s * p.stream_stride + (size_t)ch * p.channel_stride, u);
+            val = fmaxf(fabsf(x), val);
+        }
+        return __fmul_rn(val, val);
+    }
+    const float x = vsample(p, p.hist + ((size_t)s * p.cc + c) * p.W,
+                            p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride, u);
+    return (p.mode == WF_METER_RMS) ? __fmul_rn(x, x) : fabsf(x);
+}
+
+__device__ __forceinline__ float combine(int mode, float a, float b)
+{
+    return (mode == WF_METER_PEAK) ? fmaxf(a, b) : __fadd_rn(a, b);
+}
+
+__device__ __forceinline__ float warp_combine(int mode, float v)
+{
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+        v = combine(mode, v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// K1: one warp per (stream, partial channel, block)
+__global__ void meter_block_kernel(const MParams p)
+{
+    const int warps_per_cta = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)p.n_streams * p.pc * p.nblk;
+    const long long L = (long long)p.W + (long long)p.n_ticks * p.hop;
+    for(long long w = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); w < total;
+        w += (long long)gridDim.x * warps_per_cta)
+    {
+        const int j = (int)(w % p.nblk);
+        const int c = (int)((w / p.nblk) % p.pc);
+        const int s = (int)(w / ((long long)p.nblk * p.pc));
+        const long long u0 = (long long)j * kBL;
+        float acc = 0.0f;
+#pragma unroll
+        for(int k = 0; k < kBL / 32; ++k)
+        {
+            const long long u = u0 + lane + 32 * k;
+            if(u < L)
+                acc = combine(p.mode, acc, contrib(p, s, c, u));
+        }
+        acc = warp_combine(p.mode, acc);
+        if(lane == 0)
+            p.partial[w] = acc;
+    }
+}
+
+// K2: one warp per (stream, tick, partial channel): window [lo, hi) of the timeline
+__global__ void meter_window_kernel(const MParams p)
+{
+    const int warps_per_cta = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)p.n_streams * p.n_ticks * p.pc;
+    for(long long w = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); w < total;
+        w += (long long)gridDim.x * warps_per_cta)
+    {
+        const int c = (int)(w % p.pc);
+        const int t = (int)((w / p.pc) % p.n_ticks);
+        const int s = (int)(w / ((long long)p.pc * p.n_ticks));
+        const long long lo = (long long)(t + 1) * p.hop, hi = lo + p.W;
+        const long long jb = (lo + kBL - 1) / kBL, je = hi / kBL;
+        float acc = 0.0f;
+        if(jb <= je)
+        {
+            for(long long u = lo + lane; u < jb * kBL; u += 32)
+                acc = combine(p.mode, acc, contrib(p, s, c, u));
+            const float *part = p.partial + ((size_t)s * p.pc + c) * p.nblk;
+            for(long long j = jb + lane; j < je; j += 32)
+                acc = combine(p.mode, acc, part[j]);
+            for(long long u = je * kBL + lane; u < hi; u += 32)
+                acc = combine(p.mode, acc, contrib(p, s, c, u));
+        }
+        else
+        {
+            for(long long u = lo + lane; u < hi; u += 32)
+                acc = combine(p.mode, acc, contrib(p, s, c, u));
+        }
+        acc = warp_combine(p.mode, acc);
+        if(lane == 0)
+            p.raw[w] = acc;
+    }
+}
+
+// K3: one thread per stream, the per-tick recurrence (src/source_generic.cpp:232-269)
+__global__ void meter_scan_kernel(const MParams p)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= p.n_streams)
+        return;
+    if(p.mode == WF_METER_INPUT_RMS)
+    {
+        for(int t = 0; t < p.n_ticks; ++t)
+            if(p.out_lin)
+                p.out_lin[(size_t)s * p.n_ticks + t] =
+                    __fsqrt_rn(__fdiv_rn(p.raw[(size_t)s * p.n_ticks + t], (float)p.W)); // src/source_generic.cpp:402
+        return;
+    }
+    float buf[2] = {p.buf[2 * s], p.buf[2 * s + 1]};
+    bool last_silent = p.flags[s] != 0;
+    for(int t = 0; t < p.n_ticks; ++t)
+    {
+        int silent_channels = 0;
+        for(int c = 0; c < p.cc; ++c)
+        {
+            float out = p.raw[((size_t)s * p.n_ticks + t) * p.pc + c];
+            if(p.mode == WF_METER_RMS)
+                out = __fsqrt_rn(__fdiv_rn(out, (float)p.W)); // :243
+            if(p.tsmooth)
+            {
+                if(!p.fast_peaks || (out <= buf[c]))
+                    out = __fadd_rn(__fmul_rn(p.g, buf[c]), __fmul_rn(p.g2, out)); // :255-256
+            }
+            buf[c] = out;
+            const float val = (out > 0.0f) ? 20.0f * log10f(out) : p.db_min; // dbfs, src/source.hpp:293-299
+            if(val < p.floor_m10)
+                ++silent_channels;
+            const size_t o = ((size_t)s * p.n_ticks + t) * p.cc + c;
+            if(p.out_db)
+                p.out_db[o] = val;
+            if(p.out_lin)
+                p.out_lin[o] = out;
+        }
+        last_silent = silent_channels >= p.cc; // :264-269
+        if(p.out_silent)
+            p.out_silent[(size_t)s * p.n_ticks + t] = last_silent ? 1 : 0;
+    }
+    p.buf[2 * s] = buf[0];
+    p.buf[2 * s + 1] = buf[1];
+    p.flags[s] = last_silent ? 1 : 0;
+}
+
+// K4: ring for the next call = the last W samples of the timeline
+__global__ void meter_hist_kernel(const MParams p)
+{
+    const long long total = (long long)p.n_streams * p.cc * p.W;
+    const long long shift = (long long)p.n_ticks * p.hop;
+    for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    {
+        const int u = (int)(i % p.W);
+        const int c = (int)((i / p.W) % p.cc);
+        const int s = (int)(i / ((long long)p.W * p.cc));
+        p.hist_next[i] = vsample(p, p.hist + ((size_t)s * p.cc + c) * p.W,
+                                 p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride, u + shift);
+    }
+}
+
+__global__ void meter_fill_kernel(float *q, long long n, float v)
+{
+    for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        q[i] = v;
+}
+
+// timeout branch (src/source_generic.cpp:184-199) for streams [first, first+count)
+__global__ void meter_reset_kernel(float *hist, float *buf, unsigned char *flags, int first, int count, int cc, int W)
+{
+    for(int s = first + blockIdx.x; s < first + count; s += gridDim.x)
+    {
+        if(flags[s] != 0)
+            continue; // already silent: tick returns early
+        for(long long i = threadIdx.x; i < (long long)cc * W; i += blockDim.x)
+            hist[(size_t)s * cc * W + i] = 0.0f;
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            buf[2 * s] = 0.0f;
+            buf[2 * s + 1] = 0.0f;
+            flags[s] = 1;
+        }
+    }
+}
+
+} // namespace
+
+struct wf_meter {
+    wf_meter_config cfg{};
+    int device = 0, sm_count = 0;
+    int W = 0, pc = 1;
+    float db_min = 0.0f;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::string last_error;
+    int64_t launches = 0;
+    float *d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    float *d_buf = nullptr;
+    unsigned char *d_flags = nullptr;
+    // scratch / staging
+    float *d_partial = nullptr, *d_raw = nullptr, *s_pcm = nullptr, *s_db = nullptr, *s_lin = nullptr;
+    unsigned char *s_silent = nullptr;
+    size_t partial_cap = 0, raw_cap = 0, pcm_cap = 0, db_cap = 0, lin_cap = 0, silent_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_meter_create_error;
+
+int merr(wf_meter *m, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if(m)
+        m->last_error = buf;
+    else
+        g_meter_create_error = buf;
+    return code;
+}
+
+#define WFM_CUDA(m, call)                                                                                       \
+    do                                                                                                          \
+    {                                                                                                           \
+        cudaError_t _err = (call);                                                                              \
+        if(_err != cudaSuccess)                                                                                 \
+            return merr((m), (_err == cudaErrorMemoryAllocation) ? WF_ERR_OOM : WF_ERR_CUDA, "%s failed: %s", \
+                        #call, cudaGetErrorString(_err));                                                       \
+    } while(0)
+
+template<typename T>
+int mensure(wf_meter *m, T **buf, size_t *cap, size_t need)
+{
+    if(need <= *cap)
+        return WF_OK;
+    if(*buf)
+        cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    WFM_CUDA(m, cudaMalloc((void **)buf, need * sizeof(T)));
+    *cap = need;
+    return WF_OK;
+}
+
+bool m_is_device_ptr(const void *p)
+{
+    if(!p)
+        return false;
+    cudaPointerAttributes a{};
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int grid_for(long long warps, int warps_per_cta, int sm_count)
+{
+    const long long ctas = (warps + warps_per_cta - 1) / warps_per_cta;
+    return (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sm_count * 16));
+}
+
+} // namespace
+
+extern "C" {
+
+void wf_meter_config_init(wf_meter_config *c)
+{
+    memset(c, 0, sizeof(*c));
+    c->struct_size = (uint32_t)sizeof(wf_meter_config);
+    c->device = -1;
+    c->max_streams = 1;
+    c->sample_rate = 48000;
+    c->capture_channels = 2;
+    c->mode = WF_METER_RMS; // P_RMS_MODE default true, src/source.cpp:167
+    c->meter_ms = 150;      // P_METER_BUF default, src/source.cpp:166
+    c->tsmoothing = WF_TSMOOTH_EXPONENTIAL;
+    c->gravity = 0.65f;
+    c->fast_peaks = 0;
+    c->floor_db = -65;
+}
+
+const char *wf_meter_last_error(const wf_meter *m) { return m ? m->last_error.c_str() : g_meter_create_error.c_str(); }
+
+int wf_meter_create(const wf_meter_config *cfg, wf_meter **out)
+{
+    if(!cfg || !out)
+        return WF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if(cfg->struct_size != sizeof(wf_meter_config))
+        return merr(nullptr, WF_ERR_ABI, "wf_meter_config.struct_size mismatch");
+    if(cfg->capture_channels < 1 || cfg->capture_channels > 2 || cfg->max_streams < 1 || cfg->sample_rate < 16 ||
+       cfg->mode < WF_METER_PEAK || cfg->mode > WF_METER_INPUT_RMS)
+        return merr(nullptr, WF_ERR_INVALID_ARG, "bad meter config");
+    int W;
+    if(cfg->mode == WF_METER_INPUT_RMS)
+        W = (int)(cfg->sample_rate & ~15u); // m_input_rms_size, src/source.cpp:1148
+    else
+        W = (int)(((size_t)((double)cfg->sample_rate * ((double)cfg->meter_ms / 1000.0))) & ~(size_t)15); // :1121
+    if(W < 16)
+        return merr(nullptr, WF_ERR_INVALID_ARG, "meter window of %d ms is shorter than 16 samples", cfg->meter_ms);
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return merr(nullptr, WF_ERR_NO_DEVICE, "no CUDA device (the meter has no CPU fallback)");
+    }
+    int dev = cfg->device;
+    if(dev < 0 && cudaGetDevice(&dev) != cudaSuccess)
+        return merr(nullptr, WF_ERR_CUDA, "cudaGetDevice failed");
+    if(dev >= ndev)
+        return merr(nullptr, WF_ERR_INVALID_ARG, "device %d out of range", dev);
+    wf_meter *m = new(std::nothrow) wf_meter();
+    if(!m)
+        return WF_ERR_OOM;
+    m->cfg = *cfg;
+    m->device = dev;
+    m->W = W;
+    m->pc = (cfg->mode == WF_METER_INPUT_RMS) ? 1 : cfg->capture_channels;
+    m->db_min = 20.0f * log10f(1.17549435e-38f); // DB_MIN, src/source.cpp:43
+    auto bail = [&](int code) {
+        g_meter_create_error = m->last_error;
+        wf_meter_destroy(m);
+        return code;
+    };
+#define WFM_C(call)                                                                                  \
+    do                                                                                               \
+    {                                                                                                \
+        cudaError_t _err = (call);                                                                   \
+        if(_err != cudaSuccess)                                                                      \
+            return bail(merr(m, (_err == cudaErrorMemoryAllocation) ? WF_ERR_OOM : WF_ERR_CUDA, "%s: %s", #call, \
+                             cudaGetErrorString(_err)));                                             \
+    } while(0)
+    WFM_C(cudaSetDevice(dev));
+    cudaDeviceProp prop{};
+    WFM_C(cudaGetDeviceProperties(&prop, dev));
+    if(prop.major < 10)
+        return bail(merr(m, WF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                         prop.major, prop.minor));
+    m->sm_count = prop.multiProcessorCount;
+    WFM_C(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    WFM_C(cudaEventCreate(&m->ev0));
+    WFM_C(cudaEventCreate(&m->ev1));
+    const size_t S = (size_t)cfg->max_streams, hist_n = S * cfg->capture_channels * (size_t)W;
+    WFM_C(cudaMalloc((void **)&m->d_hist[0], hist_n * sizeof(float)));
+    WFM_C(cudaMalloc((void **)&m->d_hist[1], hist_n * sizeof(float)));
+    WFM_C(cudaMalloc((void **)&m->d_buf, S * 2 * sizeof(float)));
+    WFM_C(cudaMalloc((void **)&m->d_flags, S));
+    // ≙ update(): ring := 0 (src/source.cpp:1181), m_meter_buf := DB_MIN (:1124-1125, sic), m_last_silent := false (:1236)
+    WFM_C(cudaMemsetAsync(m->d_hist[0], 0, hist_n * sizeof(float), m->stream));
+    WFM_C(cudaMemsetAsync(m->d_flags, 0, S, m->stream));
+    meter_fill_kernel<<<(int)std::min<size_t>((S * 2 + 255) / 256, 1024), 256, 0, m->stream>>>(m->d_buf, (long long)S * 2,
+                                                                                              m->db_min);
+    WFM_C(cudaGetLastError());
+    m->launches++;
+    WFM_C(cudaStreamSynchronize(m->stream));
+#undef WFM_C
+    *out = m;
+    return WF_OK;
+}
+
+void wf_meter_destroy(wf_meter *m)
+{
+    if(!m)
+        return;
+    if(m->stream)
+    {
+        cudaSetDevice(m->device);
+        cudaStreamSynchronize(m->stream);
+    }
+    void *ptrs[] = {m->d_hist[0], m->d_hist[1], m->d_buf, m->d_flags, m->d_partial, m->d_raw,
+                    m->s_pcm, m->s_db, m->s_lin, m->s_silent};
+    for(void *q : ptrs)
+        if(q)
+            cudaFree(q);
+    if(m->ev0)
+        cudaEventDestroy(m->ev0);
+    if(m->ev1)
+        cudaEventDestroy(m->ev1);
+    if(m->stream)
+        cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int32_t wf_meter_window(const wf_meter *m) { return m ? m->W : 0; }
+
+int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stream)
+{
+    if(!m || !b)
+        return WF_ERR_INVALID_ARG;
+    if(b->struct_size != sizeof(wf_meter_batch))
+        return merr(m, WF_ERR_ABI, "wf_meter_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_meter_batch));
+    if(b->n_streams < 0 || b->n_ticks < 0 || b->hop < 1)
+        return merr(m, WF_ERR_INVALID_ARG, "n_streams/n_ticks must be >= 0 and hop >= 1");
+    if(b->first_stream < 0 || (int64_t)b->first_stream + b->n_streams > m->cfg.max_streams)
+        return merr(m, WF_ERR_CAPACITY, "streams [%d, %d) exceed max_streams %d", b->first_stream,
+                    b->first_stream + b->n_streams, m->cfg.max_streams);
+    if(b->n_streams == 0 || b->n_ticks == 0)
+        return WF_OK;
+    if(!b->pcm)
+        return merr(m, WF_ERR_INVALID_ARG, "pcm is null");
+    if(b->stream_stride < 0 || b->channel_stride < 0)
+        return merr(m, WF_ERR_INVALID_ARG, "negative strides are not supported");
+    if((long long)b->n_ticks * b->hop > 0x7fffffffLL - m->W)
+        return merr(m, WF_ERR_INVALID_ARG, "n_ticks * hop too large for one call");
+
+    WFM_CUDA(m, cudaSetDevice(m->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m->stream;
+    const int cc = m->cfg.capture_channels, pc = m->pc, W = m->W;
+    const size_t S = (size_t)b->n_streams, T = (size_t)b->n_ticks;
+    const long long L = (long long)W + (long long)T * b->hop;
+    const int nblk = (int)((L + kBL - 1) / kBL);
+    const bool dev_ptrs = m_is_device_ptr(b->pcm);
+    const bool is_feed = m->cfg.mode == WF_METER_INPUT_RMS;
+    const size_t out_n = S * T * (is_feed ? 1 : cc);
+
+    int rc;
+    if((rc = mensure(m, &m->d_partial, &m->partial_cap, S * pc * (size_t)nblk)))
+        return rc;
+    if((rc = mensure(m, &m->d_raw, &m->raw_cap, S * T * pc)))
+        return rc;
+    const float *d_pcm = b->pcm;
+    float *d_db = b->out_db, *d_lin = b->out_lin;
+    unsigned char *d_silent = b->out_silent;
+    if(!dev_ptrs)
+    {
+        const size_t span = (S - 1) * (size_t)b->stream_stride + (size_t)(cc - 1) * (size_t)b->channel_stride +
+                            T * (size_t)b->hop;
+        if((rc = mensure(m, &m->s_pcm, &m->pcm_cap, span)))
+            return rc;
+        WFM_CUDA(m, cudaMemcpyAsync(m->s_pcm, b->pcm, span * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_pcm = m->s_pcm;
+        if(b->out_db)
+        {
+            if((rc = mensure(m, &m->s_db, &m->db_cap, out_n)))
+                return rc;
+            d_db = m->s_db;
+        }
+        if(b->out_lin)
+        {
+            if((rc = mensure(m, &m->s_lin, &m->lin_cap, out_n)))
+                return rc;
+            d_lin = m->s_lin;
+        }
+        if(b->out_silent)
+        {
+            if((rc = mensure(m, &m->s_silent, &m->silent_cap, S * T)))
+                return rc;
+            d_silent = m->s_silent;
+        }
+    }
+
+    MParams p{};
+    p.pcm = d_pcm;
+    p.stream_stride = b->stream_stride;
+    p.channel_stride = b->channel_stride;
+    const size_t slot = (size_t)b->first_stream;
+    p.hist = m->d_hist[m->cur] + slot * cc * W;
+    p.hist_next = m->d_hist[m->cur ^ 1] + slot * cc * W;
+    p.partial = m->d_partial;
+    p.raw = m->d_raw;
+    p.buf = m->d_buf + slot * 2;
+    p.flags = m->d_flags + slot;
+    p.out_db = is_feed ? nullptr : d_db;
+    p.out_lin = d_lin;
+    p.out_silent = is_feed ? nullptr : d_silent;
+    p.n_streams = b->n_streams;
+    p.n_ticks = b->n_ticks;
+    p.hop = b->hop;
+    p.W = W;
+    p.cc = cc;
+    p.pc = pc;
+    p.nblk = nblk;
+    p.mode = m->cfg.mode;
+    {
+        wf_config gc{};
+        gc.tsmoothing = m->cfg.tsmoothing;
+        gc.gravity = m->cfg.gravity;
+        p.g = (m->cfg.tsmoothing == WF_TSMOOTH_NONE) ? 0.0f : wf::gravity_for(gc, b->seconds);
+    }
+    p.g2 = 1.0f - p.g;
+    p.tsmooth = m->cfg.tsmoothing != WF_TSMOOTH_NONE;
+    p.fast_peaks = m->cfg.fast_peaks;
+    p.floor_m10 = (float)(m->cfg.floor_db - 10);
+    p.db_min = m->db_min;
+
+    WFM_CUDA(m, cudaEventRecord(m->ev0, st));
+    constexpr int kWarps = 8;
+    meter_block_kernel<<<grid_for((long long)S * pc * nblk, kWarps, m->sm_count), kWarps * 32, 0, st>>>(p);
+    WFM_CUDA(m, cudaGetLastError());
+    meter_window_kernel<<<grid_for((long long)S * T * pc, kWarps, m->sm_count), kWarps * 32, 0, st>>>(p);
+    WFM_CUDA(m, cudaGetLastError());
+    meter_scan_kernel<<<(int)((S + 127) / 128), 128, 0, st>>>(p);
+    WFM_CUDA(m, cudaGetLastError());
+    {
+        const long long total = (long long)S * cc * W;
+        meter_hist_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)m->sm_count * 16), 256, 0, st>>>(p);
+        WFM_CUDA(m, cudaGetLastError());
+    }
+    m->launches += 4;
+    WFM_CUDA(m, cudaEventRecord(m->ev1, st));
+    m->ev_valid = true;
+    // The ring is double-buffered per ENGINE, so a call must cover every stream whose history should survive: copy the
+    // untouched streams' rings across before flipping (cheap: only when a call addresses a subset of the streams).
+    if(b->n_streams != m->cfg.max_streams)
+    {
+        const size_t per = (size_t)cc * W * sizeof(float);
+        if(slot > 0)
+            WFM_CUDA(m, cudaMemcpyAsync(m->d_hist[m->cur ^ 1], m->d_hist[m->cur], slot * per, cudaMemcpyDeviceToDevice, st));
+        const size_t after = slot + S;
+        if(after < (size_t)m->cfg.max_streams)
+            WFM_CUDA(m, cudaMemcpyAsync(m->d_hist[m->cur ^ 1] + after * cc * W, m->d_hist[m->cur] + after * cc * W,
+                                        ((size_t)m->cfg.max_streams - after) * per, cudaMemcpyDeviceToDevice, st));
+    }
+    m->cur ^= 1;
+    if(!dev_ptrs)
+    {
+        if(b->out_db && !is_feed)
+            WFM_CUDA(m, cudaMemcpyAsync(b->out_db, d_db, out_n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if(b->out_lin)
+            WFM_CUDA(m, cudaMemcpyAsync(b->out_lin, d_lin, out_n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if(b->out_silent && !is_feed)
+            WFM_CUDA(m, cudaMemcpyAsync(b->out_silent, d_silent, S * T, cudaMemcpyDeviceToHost, st));
+    }
+    return WF_OK;
+}
+
+int wf_meter_process(wf_meter *m, const wf_meter_batch *b)
+{
+    int rc = wf_meter_process_async(m, b, nullptr);
+    if(rc)
+        return rc;
+    WFM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return WF_OK;
+}
+
+int wf_meter_reset(wf_meter *m, int32_t first, int32_t count)
+{
+    if(!m)
+        return WF_ERR_INVALID_ARG;
+    if(first < 0 || count < 0 || (int64_t)first + count > m->cfg.max_streams)
+        return merr(m, WF_ERR_CAPACITY, "reset range out of bounds");
+    if(count == 0)
+        return WF_OK;
+    WFM_CUDA(m, cudaSetDevice(m->device));
+    meter_reset_kernel<<<std::min(count, m->sm_count * 4), 256, 0, m->stream>>>(m->d_hist[m->cur], m->d_buf, m->d_flags, first,
+                                                                             count, m->cfg.capture_channels, m->W);
+    WFM_CUDA(m, cudaGetLastError());
+    m->launches++;
+    WFM_CUDA(m, cudaStreamSynchronize(m->stream));
+    return WF_OK;
+}
+
+int64_t wf_meter_launch_count(const wf_meter *m) { return m ? m->launches : 0; }
+
+float wf_meter_last_kernel_ms(wf_meter *m)
+{
+    if(!m || !m->ev_valid || cudaEventSynchronize(m->ev1) != cudaSuccess)
+        return -1.0f;
+    float ms = -1.0f;
+    if(cudaEventElapsedTime(&ms, m->ev0, m->ev1) != cudaSuccess)
+        return -1.0f;
+    return ms;
+}
+
+} // extern "C"

@@ -1,0 +1,641 @@
+// wf_v3.cuh — the fused spectrum pipeline for fft sizes 4096 / 8192 / 16384: one CTA per tick, a cluster of R CTAs
+// (R = 1, 2, 4, 8) per stream, and a three-pass register FFT whose every shared-memory access is base + immediate.
+//
+// ncu on the first-generation kernels (profiles/r01i_generic8192.txt) showed 16 750 warp-instructions per N=8192 frame,
+// only ~5 000 of them floating point: Stockham index arithmetic (LEA/IMAD/ISETP), run-time flag tests and twiddle loads
+// through computed global addresses dominated, with 7 block barriers per frame.  This kernel restructures the same
+// mathematics so that the integer work disappears:
+//
+//   * the N/2-point complex FFT is a 3-D decimation: M = A*B*C, input n = a*BC + b*C + c, output k = ka + A*kb + AB*kc;
+//     each pass is a register DFT along one axis (radix A, B, C = 16/32, 16, 8/16) and between passes the data crosses
+//     shared memory in layouts chosen so that thread->address is (one base register) + (compile-time offset) and every
+//     64-bit access is bank-conflict free:   L1[ka][b][c] (stride BC+pad)  ->  L2[kb][ka][c] (strides A*(C+1), C+1)  ->  X[k];
+//   * inter-pass twiddles come from two small tables laid out [index][thread] (tw1[ka][t] = W_M^(t*ka), tw2[kb][c] =
+//     W_BC^(c*kb)), i.e. again base + immediate, coalesced, L1-resident;
+//   * the real-FFT split pass handles bins k and M-k together (one twiddle multiply for two bins, as wf_fast2048.cuh);
+//   * rarely used features (slope, roll-off, volume, fast peaks, skip mask, peak output) are compiled out by template.
+//
+// Work decomposition is that of wf_wide.cuh (which this kernel supersedes for these sizes): per round of R ticks, CTA r
+// transforms tick t0+r, the linear magnitudes are exchanged through distributed shared memory so that CTA q owns bins
+// [q*B/R, (q+1)*B/R) of all R ticks, and walks them through the ticks in order with the EMA state in registers.  R = 1
+// needs no exchange: the EMA runs on the registers the split pass produced.  HBM traffic is the algorithmic minimum.
+// Reference semantics: src/source_generic.cpp:26-180 (see wf_kernels.cuh for the line-by-line citations).
+#pragma once
+#include "wf_kernels.cuh"
+#include "wf_wide.cuh"
+
+namespace wf {
+namespace v3 {
+
+template<int N> struct Plan3;
+template<> struct Plan3<4096> { static constexpr int A = 16, B = 16, C = 8; };
+template<> struct Plan3<8192> { static constexpr int A = 16, B = 16, C = 16; };
+template<> struct Plan3<16384> { static constexpr int A = 32, B = 16, C = 16; };
+
+template<int N>
+struct Geo3 {
+    static constexpr int M = N / 2;
+    static constexpr int A = Plan3<N>::A, B = Plan3<N>::B, C = Plan3<N>::C;
+    static_assert(A * B * C == M, "plan does not factor N/2");
+    static constexpr int TN = B * C;  // threads per CTA = lines of pass 1
+    static constexpr int P = A;       // complex points (= bins) per thread
+    static constexpr int LB = A / B;  // lines per thread in pass 2 (A*C lines of B points)
+    static constexpr int LC = A / C;  // lines per thread in pass 3 (A*B lines of C points)
+    static_assert(LB >= 1 && LC >= 1 && TN % A == 0, "plan shape");
+    static constexpr int S1 = B * C + ((C < 16) ? C : 0); // L1 stride per ka (padding keeps half-warps conflict free)
+    static constexpr int SA = C + 1;                      // L2 stride per ka
+    static constexpr int SB = A * SA;                     // L2 stride per kb
+    static constexpr int L1_ELEMS = A * S1;
+    static constexpr int L2_ELEMS = B * SB;
+    static constexpr int BUF = (L1_ELEMS > L2_ELEMS ? L1_ELEMS : L2_ELEMS); // one buffer serves L1, L2, X and the inbox
+    static constexpr int MINB = (512 / TN) > 0 ? (512 / TN) : 1;
+};
+
+struct Tw3 {
+    const float2 *tw1; // [A][TN]  W_M^(t*ka)
+    const float2 *tw2; // [B][C]   W_(B*C)^(c*kb)
+};
+
+// dynamic shared memory of one CTA
+template<int N>
+constexpr size_t smem_bytes(int dch, int n_points, bool display)
+{
+    size_t b = (size_t)Geo3<N>::BUF * sizeof(float2);
+    if(display)
+        b += (size_t)dch * (N / 2) * sizeof(float) + (size_t)4 * n_points * sizeof(float);
+    return b;
+}
+
+// ---- the 3-pass FFT: v[a] = x[a*BC + tid] (windowed) on entry; on exit X[k] sits in buf[k] (natural order) -------
+template<int N>
+struct Fft3 {
+    using G = Geo3<N>;
+    static constexpr int M = G::M, A = G::A, B = G::B, C = G::C, TN = G::TN, P = G::P;
+
+    static __device__ __forceinline__ void load_raw(float2 (&v)[P], const float *frame, int aligned8, int tid)
+    {
+        if(aligned8)
+        {
+            const float2 *f2 = reinterpret_cast<const float2 *>(frame) + tid;
+#pragma unroll
+            for(int a = 0; a < A; ++a)
+                v[a] = ldg_stream_f2(f2 + a * TN);
+        }
+        else
+        {
+            const float *f1 = frame + 2 * tid;
+#pragma unroll
+            for(int a = 0; a < A; ++a)
+                v[a] = make_float2(ldg_stream_f1(f1 + 2 * a * TN), ldg_stream_f1(f1 + 2 * a * TN + 1));
+        }
+    }
+    // non-zero test (src/source_generic.cpp:63-76) + window multiply (:97-103); returns "any sample non-zero" (this thread)
+    static __device__ __forceinline__ bool finish_load(pk::c64 (&x)[P], const float2 (&v)[P], const float2 *window2, int tid)
+    {
+        unsigned long long nzbits = 0;
+#pragma unroll
+        for(int a = 0; a < A; ++a)
+        {
+            x[a] = pk::from(v[a]);
+            nzbits |= x[a];
+        }
+        if(window2 != nullptr)
+        {
+            const pk::c64 *w = reinterpret_cast<const pk::c64 *>(window2) + tid;
+#pragma unroll
+            for(int a = 0; a < A; ++a)
+                x[a] = pk::mul(x[a], __ldg(w + a * TN));
+        }
+        return (nzbits & 0x7fffffff7fffffffull) != 0ull;
+    }
+
+    // nz_thread: this thread saw a non-zero sample; returns the block-wide OR (folded into the first barrier)
+    static __device__ __forceinline__ bool run(pk::c64 (&x)[P], float2 *buf, const Tw3 &tw, int tid, bool nz_thread)
+    {
+        pk::c64 *b64 = reinterpret_cast<pk::c64 *>(buf);
+        bool nz;
+        // ---- pass 1: DFT over a (stride BC), twiddle W_M^(tid*ka), store L1[ka][b][c] at tid + ka*S1 ----
+        pk::dft_bitrev<A>(x);
+        {
+            const pk::c64 *t1 = reinterpret_cast<const pk::c64 *>(tw.tw1) + tid;
+            nz = __syncthreads_or(nz_thread ? 1 : 0) != 0; // previous users of the buffer are done
+#pragma unroll
+            for(int ka = 0; ka < A; ++ka)
+            {
+                pk::c64 y = x[bitrev<A>(ka)];
+                if(ka > 0)
+                    y = pk::cmul(y, __ldg(t1 + ka * TN));
+                b64[tid + ka * G::S1] = y;
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: lines (ka, c), c fastest; line l = tid + q*TN -> ka = tid/C + q*B, c = tid%C ----
+        {
+            const int c = tid % C;
+            const pk::c64 *src = b64 + (tid / C) * G::S1 + c;
+#pragma unroll
+            for(int q = 0; q < G::LB; ++q)
+#pragma unroll
+                for(int b = 0; b < B; ++b)
+                    x[q * B + b] = src[q * B * G::S1 + b * C];
+            __syncthreads(); // L1 fully read before L2 (same memory) is written
+            const pk::c64 *t2 = reinterpret_cast<const pk::c64 *>(tw.tw2) + c;
+            pk::c64 *dst = b64 + (tid / C) * G::SA + c;
+#pragma unroll
+            for(int q = 0; q < G::LB; ++q)
+            {
+                pk::c64 y[B];
+#pragma unroll
+                for(int b = 0; b < B; ++b)
+                    y[b] = x[q * B + b];
+                pk::dft_bitrev<B>(y);
+#pragma unroll
+                for(int kb = 0; kb < B; ++kb)
+                {
+                    pk::c64 z = y[bitrev<B>(kb)];
+                    if(kb > 0)
+                        z = pk::cmul(z, __ldg(t2 + kb * C));
+                    dst[q * B * G::SA + kb * G::SB] = z; // L2[kb][ka][c]
+                }
+            }
+        }
+        __syncthreads();
+        // ---- pass 3: lines (ka, kb), ka fastest; line l = tid + q*TN -> ka = tid%A, kb = tid/A + q*TN/A ----
+        {
+            const pk::c64 *src = b64 + (tid / A) * G::SB + (tid % A) * G::SA;
+#pragma unroll
+            for(int q = 0; q < G::LC; ++q)
+#pragma unroll
+                for(int c = 0; c < C; ++c)
+                    x[q * C + c] = src[q * (TN / A) * G::SB + c];
+            __syncthreads(); // L2 fully read before X (same memory) is written
+#pragma unroll
+            for(int q = 0; q < G::LC; ++q)
+            {
+                pk::c64 y[C];
+#pragma unroll
+                for(int c = 0; c < C; ++c)
+                    y[c] = x[q * C + c];
+                pk::dft_bitrev<C>(y);
+#pragma unroll
+                for(int kc = 0; kc < C; ++kc)
+                    b64[tid + q * TN + kc * (A * B)] = y[bitrev<C>(kc)]; // X[ka + A*kb + AB*kc]
+            }
+        }
+        __syncthreads();
+        return nz;
+    }
+};
+
+} // namespace v3
+
+// EXTRA compiles in slope / fast peaks / skip mask / volume normalisation / roll-off / peak output.
+template<int N, int CC, int R, bool EXTRA>
+__global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
+    stft_v3_kernel(const __grid_constant__ KParams p, const __grid_constant__ v3::Tw3 tw)
+{
+    using namespace wide;
+    using G = v3::Geo3<N>;
+    using F = v3::Fft3<N>;
+    constexpr int M = G::M, B = G::M, TN = G::TN, P = G::P;
+    constexpr int HP = P / 2;      // pairs (k, M-k) per thread
+    constexpr int SLICE = B / R;   // bins owned by one CTA
+    constexpr int SP = SLICE / TN; // bins owned by one thread
+    static_assert(SP >= 1 && SP * TN * R == B, "cluster size does not tile the bins");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    float *inbox = reinterpret_cast<float *>(smem_raw);       // [R][CC][SLICE] linear magnitudes (after barrier A)
+    float *dbfull = reinterpret_cast<float *>(buf + G::BUF); // [dch][B] dB spectrum of MY tick (display mode)
+    float *pts = dbfull + (size_t)p.dch * B;
+    __shared__ float red_scratch[2 * TN];
+    __shared__ unsigned nzf[R];
+    __shared__ unsigned redf[2][R];
+
+    const int tid = threadIdx.x;
+    const unsigned r = (R > 1) ? cluster_ctarank() : 0u;
+    const int s = blockIdx.x / R;
+    const int T = p.n_frames;
+    const int dch = p.dch, och = p.och;
+    const bool stereo = p.stereo != 0;
+    const bool want_points = (p.out_points != nullptr) || (p.out_pixels != nullptr) || (p.out_min != nullptr);
+    const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
+    const uint32_t inbox_sa = smem_u32(inbox);
+    const uint32_t dbfull_sa = smem_u32(dbfull);
+
+    // Bin bookkeeping.  Phase 1 produces, per thread, the pairs j < HP:  k1 = tid + j*TN  and  k2 = M - k1
+    // (thread 0, j = 0: k2 := M/2, the self-paired bin; bin M itself does not exist).
+    // R == 1: the EMA runs directly on those registers, state index i = 2*j (+1 for k2).
+    // R  > 1: a thread owns bins r*SLICE + tid + i*TN, i < SP, fed through the inbox.
+    const int k2_first = (tid == 0) ? M / 2 : M - tid; // partner of k1 = tid (pair j = 0)
+    const int k2_base = M - tid;                      // partner of k1 = tid + j*TN is k2_base - j*TN for j >= 1
+    auto bin_of = [&](int i) -> int {
+        if constexpr(R == 1)
+        {
+            const int j = i >> 1;
+            if((i & 1) == 0)
+                return tid + j * TN;
+            return (j == 0) ? k2_first : k2_base - j * TN;
+        }
+        else
+            return (int)r * SLICE + tid + i * TN;
+    };
+    constexpr int NST = (R == 1) ? P : SP;
+
+    float st[CC][NST];
+    {
+        const float *sp = p.state + (size_t)s * CC * B;
+#pragma unroll
+        for(int c = 0; c < CC; ++c)
+#pragma unroll
+            for(int i = 0; i < NST; ++i)
+                st[c][i] = sp[c * B + bin_of(i)];
+    }
+    const unsigned char fl = p.flags[s];
+    bool last_silent = (fl & 1u) != 0;
+    bool po0 = (fl & 2u) != 0, po1 = (fl & 4u) != 0;
+    bool po_valid = true;
+    bool part0 = true, part1 = true;
+    unsigned red_par = 0;
+
+    const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
+    float *hold_s = p.hold_db + (size_t)s * och * B;
+
+    auto cl_arrive = [&]() {
+        if constexpr(R > 1)
+            cluster_arrive();
+    };
+    auto cl_wait = [&]() {
+        if constexpr(R > 1)
+            cluster_wait();
+        else
+            __syncthreads();
+    };
+
+    // cluster-wide AND of the per-thread partial "outputs <= floor-10" flags of the last tick that produced outputs
+    auto ensure_po_valid = [&]() {
+        if(po_valid)
+            return;
+        const int a0 = __syncthreads_and(part0 ? 1 : 0);
+        const int a1 = __syncthreads_and(part1 ? 1 : 0);
+        if constexpr(R > 1)
+        {
+            if(tid < R)
+                st_cluster_u32(mapa(smem_u32(&redf[red_par][r]), (unsigned)tid), (unsigned)((a0 ? 1 : 0) | (a1 ? 2 : 0)));
+            cluster_arrive();
+            cluster_wait();
+            unsigned all = 3u;
+#pragma unroll
+            for(int q = 0; q < R; ++q)
+                all &= redf[red_par][q];
+            po0 = (all & 1u) != 0;
+            if(dch > 1)
+                po1 = (all & 2u) != 0;
+            red_par ^= 1u;
+        }
+        else
+        {
+            po0 = a0 != 0;
+            if(dch > 1)
+                po1 = a1 != 0;
+        }
+        po_valid = true;
+    };
+
+    float2 v[P];
+    if((int)r < T)
+        F::load_raw(v, pcm_s + (size_t)r * p.hop, p.aligned8, tid);
+
+    for(int t0 = 0; t0 < T; t0 += R)
+    {
+        const int nf = min(R, T - t0);
+        const bool mine = (int)r < nf;
+        float magr[CC][P]; // [c][2*j] = |X[k1]|, [c][2*j+1] = |X[k2]| (normalised, slope applied)
+        unsigned nzbits = 0;
+
+        // ---- phase 1: window, FFT, split pass, magnitude of my tick (src/source_generic.cpp:97-122) ----
+        if(mine)
+        {
+#pragma unroll
+            for(int c = 0; c < CC; ++c)
+            {
+                if(c > 0)
+                    F::load_raw(v, pcm_s + (size_t)c * p.channel_stride + (size_t)(t0 + r) * p.hop, p.aligned8, tid);
+                pk::c64 x[P];
+                const bool nzt = F::finish_load(x, v, p.window2, tid);
+                const bool nz = F::run(x, buf, tw, tid, nzt);
+                nzbits |= nz ? (1u << c) : 0u;
+                const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);
+                const pk::c64 *twp = reinterpret_cast<const pk::c64 *>(p.tw_post) + tid;
+                const pk::c64 ch2 = pk::make(p.coef_half, p.coef_half);
+#pragma unroll
+                for(int j = 0; j < HP; ++j)
+                {
+                    const int k1 = tid + j * TN;
+                    const pk::c64 a = X[k1];
+                    // X[M - k1]: descending addresses (conflict free); thread 0 pairs bin 0 with itself
+                    const pk::c64 bq = X[(j == 0 && tid == 0) ? 0 : (M - k1)];
+                    const pk::c64 b = pk::conj(bq);
+                    const pk::c64 sum = pk::add(a, b);
+                    const pk::c64 o = pk::mul_neg_i(pk::sub(a, b));
+                    const pk::c64 wo = pk::cmul(o, __ldg(twp + j * TN));
+                    const pk::c64 y1 = pk::add(sum, wo);
+                    const pk::c64 y2 = pk::sub(sum, wo);
+                    const pk::c64 s1 = pk::mul(y1, y1), s2 = pk::mul(y2, y2);
+                    float p1 = pk::re(s1) + pk::im(s1);
+                    float p2 = pk::re(s2) + pk::im(s2);
+                    if(j == 0)
+                    {
+                        // thread 0: second slot = bin M/2, whose split pass is 2*conj(X[M/2])
+                        const pk::c64 xm = X[M / 2];
+                        const pk::c64 sq = pk::mul(xm, xm);
+                        const float pm = 4.0f * (pk::re(sq) + pk::im(sq));
+                        p2 = (tid == 0) ? pm : p2;
+                    }
+                    pk::c64 m = pk::mul(pk::make(sqrt_mufu(p1), sqrt_mufu(p2)), ch2);
+                    if(EXTRA && p.slope != nullptr)
+                    {
+                        const int k2 = (k1 == 0) ? M / 2 : M - k1;
+                        m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + k2)));
+                    }
+                    pk::split(m, magr[c][2 * j], magr[c][2 * j + 1]);
+                }
+            }
+        }
+
+        if constexpr(R > 1)
+        {
+            __syncthreads(); // my FFT buffer is free: it becomes the inbox
+            cluster_arrive(); // barrier A
+            cluster_wait();
+            // ---- phase 2: all-to-all through distributed shared memory ----
+            if(mine)
+            {
+                // blocks of TN bins: k1 lies in block j, k2 in block P-1-j (thread 0: k2 = M - j*TN opens block P-j, or M/2)
+                const int t0off = (tid == 0) ? 0 : TN - tid;
+#pragma unroll
+                for(int c = 0; c < CC; ++c)
+#pragma unroll
+                    for(int j = 0; j < HP; ++j)
+                    {
+                        const uint32_t d1 = mapa(inbox_sa, (unsigned)(j / SP)) +
+                                            (uint32_t)(((r * CC + c) * SLICE + tid + (j % SP) * TN) * sizeof(float));
+                        st_cluster_f32(d1, magr[c][2 * j]);
+                        const int blk = (tid == 0) ? ((j == 0) ? HP : P - j) : (P - 1 - j);
+                        const uint32_t d2 = mapa(inbox_sa, (unsigned)(blk / SP)) +
+                                            (uint32_t)(((r * CC + c) * SLICE + t0off + (blk % SP) * TN) * sizeof(float));
+                        st_cluster_f32(d2, magr[c][2 * j + 1]);
+                    }
+                if(tid < R)
+                    st_cluster_u32(mapa(smem_u32(&nzf[r]), (unsigned)tid), nzbits);
+            }
+            cluster_arrive(); // barrier B
+            if(t0 + R + (int)r < T)
+                F::load_raw(v, pcm_s + (size_t)(t0 + R + r) * p.hop, p.aligned8, tid);
+            cluster_wait();
+        }
+        else
+        {
+            if(tid == 0)
+                nzf[0] = nzbits;
+            if(t0 + 1 < T)
+                F::load_raw(v, pcm_s + (size_t)(t0 + 1) * p.hop, p.aligned8, tid);
+            __syncthreads();
+        }
+
+        // ---- phase 3: my bins through the round's ticks, in order ----
+        for(int f = 0; f < nf; ++f)
+        {
+            const int t = t0 + f;
+            const unsigned nzb = nzf[f];
+            const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
+            bool proc[2] = {false, false};
+            unsigned silent_channels = 0;
+            const float *prev_db =
+                (p.out_db != nullptr && t > 0) ? p.out_db + ((size_t)s * T + (t - 1)) * dch * B : hold_s;
+
+#pragma unroll
+            for(int c = 0; c < CC; ++c)
+            {
+                // gate, src/source_generic.cpp:63-95
+                bool do_proc = !skip_all;
+                if(!skip_all)
+                {
+                    const bool silent = ((nzb >> c) & 1u) == 0;
+                    if(!silent)
+                        last_silent = false;
+                    if(silent && p.gate)
+                    {
+                        if(last_silent)
+                            do_proc = false;
+                        else
+                        {
+                            bool outsilent;
+                            if(!stereo && c == 1 && proc[0])
+                                outsilent = false;
+                            else
+                            {
+                                ensure_po_valid();
+                                outsilent = (stereo && c == 1) ? po1 : po0;
+                            }
+                            if(outsilent)
+                            {
+                                if(++silent_channels >= (unsigned)CC)
+                                    last_silent = true;
+                                do_proc = false;
+                            }
+                        }
+                    }
+                }
+                proc[c] = do_proc;
+                // EMA, src/source_generic.cpp:124-132
+#pragma unroll
+                for(int i = 0; i < NST; ++i)
+                {
+                    float mag;
+                    if constexpr(R == 1)
+                        mag = magr[c][i];
+                    else
+                        mag = inbox[(f * CC + c) * SLICE + tid + i * TN];
+                    if(p.tsmooth)
+                    {
+                        float oldval = st[c][i];
+                        if(EXTRA && p.fast_peaks)
+                            oldval = fmaxf(mag, oldval);
+                        mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+                    }
+                    if(do_proc)
+                        st[c][i] = mag;
+                }
+            }
+
+            // ---- outputs, src/source_generic.cpp:136-179 ----
+            float vc = 0.0f;
+            if(EXTRA && p.normalize)
+            {
+                const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + t] : 0.0f;
+                vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
+            }
+            float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * T + t) * dch * B : nullptr;
+            uint32_t gather_sa = 0u;
+            if(R > 1 && want_points)
+                gather_sa = mapa(dbfull_sa, (unsigned)f);
+            float peak = -INFINITY;
+            bool outs0 = true, outs1 = true;
+            // one output value: common tail of both paths below
+            auto emit = [&](int d, int k, float outv, bool &outs) {
+                outs &= !(outv > p.floor_m10);
+                if(EXTRA && k >= 1)
+                    peak = fmaxf(peak, outv);
+                if(odb != nullptr)
+                    stg_stream(odb + d * B + k, outv);
+                if(mirror_each_frame)
+                    hold_s[d * B + k] = outv;
+                if(want_points)
+                {
+                    if constexpr(R > 1)
+                        st_cluster_f32(gather_sa + (uint32_t)((d * B + k) * sizeof(float)), outv);
+                    else
+                        dbfull[d * B + k] = outv;
+                }
+            };
+            auto finish = [&](float in, int k) -> float {
+                float outv = dbfs_mufu(in, p.db_min);
+                if(EXTRA && k >= 1)
+                {
+                    if(p.normalize)
+                        outv += vc; // :161-167
+                    if(p.rolloff != nullptr)
+                        outv = fmaxf(outv - __ldg(p.rolloff + k), p.db_min); // :169-179
+                }
+                return outv;
+            };
+            const bool all_proc = proc[0] && (CC == 1 || proc[1]);
+            if(!last_silent && all_proc)
+            {
+                // ---- hot path: every channel processed this tick — straight-line code ----
+                for(int d = 0; d < dch; ++d)
+                {
+                    bool outs = true;
+#pragma unroll
+                    for(int i = 0; i < NST; ++i)
+                    {
+                        float in;
+                        if(CC == 2 && !stereo)
+                            in = (st[0][i] + st[CC - 1][i]) * 0.5f; // :150-154
+                        else
+                            in = (CC == 2 && d == 1) ? st[CC - 1][i] : st[0][i];
+                        const int k = bin_of(i);
+                        emit(d, k, finish(in, k), outs);
+                    }
+                    if(d == 0)
+                        outs0 = outs;
+                    else
+                        outs1 = outs;
+                }
+            }
+            else
+            {
+                // ---- rare paths: tick returned early (hold, :138-139) or a channel was skipped (stale dB re-converted) ----
+                for(int d = 0; d < dch; ++d)
+                {
+                    bool outs = true;
+#pragma unroll 1
+                    for(int i = 0; i < NST; ++i)
+                    {
+                        const int k = bin_of(i);
+                        float s0 = 0.0f, s1 = 0.0f; // st[.][i] with a run-time i: select without local-memory indexing
+#pragma unroll
+                        for(int ii = 0; ii < NST; ++ii)
+                            if(ii == i)
+                            {
+                                s0 = st[0][ii];
+                                s1 = st[CC - 1][ii];
+                            }
+                        float outv;
+                        if(last_silent)
+                            outv = prev_db[d * B + k];
+                        else
+                        {
+                            float in;
+                            if(CC == 2 && !stereo)
+                            {
+                                const float in0 = proc[0] ? s0 : prev_db[k];
+                                in = (in0 + s1) * 0.5f;
+                            }
+                            else
+                            {
+                                const int c = (CC == 2) ? d : 0;
+                                in = proc[c] ? ((c == 0) ? s0 : s1) : prev_db[c * B + k];
+                            }
+                            outv = finish(in, k);
+                        }
+                        emit(d, k, outv, outs);
+                    }
+                    if(d == 0)
+                        outs0 = outs;
+                    else
+                        outs1 = outs;
+                }
+            }
+            if(!last_silent && p.gate)
+            {
+                part0 = outs0;
+                part1 = outs1;
+                po_valid = false;
+            }
+            if(p.out_silent != nullptr && r == 0 && tid == 0)
+                p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
+            if(EXTRA && p.out_peak != nullptr)
+            {
+                const float gm = group_max<TN>(peak, red_scratch);
+                if(tid == 0)
+                    atomic_max_float(p.out_peak + t, gm);
+            }
+        }
+
+        // ---- phase 4: render-time stages of my tick from the gathered dB spectrum ----
+        if(want_points)
+        {
+            cl_arrive(); // barrier C
+            cl_wait();
+            if(mine)
+                display_stage<TN>(p, dbfull, pts, B, dch, (size_t)s * T + t0 + r, tid, true, red_scratch);
+        }
+        // (the next round's FFT starts with a block barrier before it overwrites the buffer)
+    }
+
+    // ---- state back to the engine (my bins) ----
+    ensure_po_valid();
+    {
+        float *sp = p.state + (size_t)s * CC * B;
+#pragma unroll
+        for(int c = 0; c < CC; ++c)
+#pragma unroll
+            for(int i = 0; i < NST; ++i)
+                sp[c * B + bin_of(i)] = st[c][i];
+        if(p.write_hold && p.out_db != nullptr && T > 0)
+        {
+            const float *last = p.out_db + ((size_t)s * T + (T - 1)) * dch * B;
+            for(int d = 0; d < dch; ++d)
+#pragma unroll
+                for(int i = 0; i < NST; ++i)
+                    hold_s[d * B + bin_of(i)] = last[d * B + bin_of(i)];
+        }
+        if(CC == 2 && !stereo && p.write_hold)
+        {
+#pragma unroll
+            for(int i = 0; i < NST; ++i)
+                hold_s[B + bin_of(i)] = st[1][i];
+        }
+        if(r == 0 && tid == 0)
+            p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (po0 ? 2u : 0u) | (po1 ? 4u : 0u));
+    }
+    if constexpr(R > 1)
+    {
+        cluster_arrive(); // no CTA may exit while a peer can still address its shared memory
+        cluster_wait();
+    }
+}
+
+} // namespace wf

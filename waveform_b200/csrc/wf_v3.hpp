@@ -1,0 +1,18 @@
+// wf_v3.hpp — host interface of the CTA-per-tick kernel for fft sizes 4096 / 8192 / 16384 (wf_v3.cuh)
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include <vector>
+
+namespace wf {
+struct KParams;
+bool v3_supported(int N);
+int v3_min_cluster(int N); // smallest supported cluster size (1, or 2 where the per-thread state would not fit registers)
+size_t v3_smem_bytes(int N, int dch, int n_points, bool display);
+// Inter-pass twiddle tables (interleaved re,im), evaluated in double: tw1[ka][t] = W_M^(t*ka), tw2[kb][c] = W_(BC)^(c*kb)
+void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2);
+// R = CTAs per stream (1 = no cluster); extra = slope / fast peaks / skip mask / volume / roll-off / peak output in use
+cudaError_t v3_launch(int N, int cc, int R, bool extra, const KParams &kp, const float *d_tw1, const float *d_tw2,
+                      cudaStream_t st, bool display, int device);
+} // namespace wf

@@ -43,7 +43,28 @@ EXPORTS = [
     "wf_abi_version", "wf_strerror", "wf_last_error", "wf_config_init", "wf_create", "wf_destroy", "wf_get_info",
     "wf_get_table", "wf_gravity", "wf_process", "wf_process_async", "wf_synchronize", "wf_reset_state",
     "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_preview_table",
+    "wf_meter_config_init", "wf_meter_create", "wf_meter_destroy", "wf_meter_last_error", "wf_meter_window",
+    "wf_meter_process", "wf_meter_process_async", "wf_meter_reset", "wf_meter_launch_count", "wf_meter_last_kernel_ms",
 ]
+
+METER_PEAK, METER_RMS, METER_INPUT_RMS = 0, 1, 2
+
+
+class WfMeterConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_streams", C.c_int32), ("sample_rate", C.c_uint32),
+        ("capture_channels", C.c_int32), ("mode", C.c_int32), ("meter_ms", C.c_int32), ("tsmoothing", C.c_int32),
+        ("gravity", C.c_float), ("fast_peaks", C.c_int32), ("floor_db", C.c_int32),
+    ]
+
+
+class WfMeterBatch(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("n_streams", C.c_int32), ("n_ticks", C.c_int32), ("hop", C.c_int32),
+        ("first_stream", C.c_int32), ("seconds", C.c_float),
+        ("pcm", C.c_void_p), ("stream_stride", C.c_int64), ("channel_stride", C.c_int64),
+        ("out_db", C.c_void_p), ("out_lin", C.c_void_p), ("out_silent", C.c_void_p),
+    ]
 
 
 class WfConfig(C.Structure):
@@ -130,6 +151,20 @@ def load_library():
     L.wf_launch_count.argtypes = [vp]
     L.wf_last_kernel_ms.restype = C.c_float
     L.wf_last_kernel_ms.argtypes = [vp]
+    L.wf_meter_config_init.argtypes = [C.POINTER(WfMeterConfig)]
+    L.wf_meter_create.argtypes = [C.POINTER(WfMeterConfig), C.POINTER(vp)]
+    L.wf_meter_destroy.argtypes = [vp]
+    L.wf_meter_last_error.restype = C.c_char_p
+    L.wf_meter_last_error.argtypes = [vp]
+    L.wf_meter_window.restype = C.c_int32
+    L.wf_meter_window.argtypes = [vp]
+    L.wf_meter_process.argtypes = [vp, C.POINTER(WfMeterBatch)]
+    L.wf_meter_process_async.argtypes = [vp, C.POINTER(WfMeterBatch), vp]
+    L.wf_meter_reset.argtypes = [vp, C.c_int32, C.c_int32]
+    L.wf_meter_launch_count.restype = C.c_int64
+    L.wf_meter_launch_count.argtypes = [vp]
+    L.wf_meter_last_kernel_ms.restype = C.c_float
+    L.wf_meter_last_kernel_ms.argtypes = [vp]
     _lib = L
     return L
 
@@ -387,3 +422,102 @@ class Engine:
         S, T, dch, row = data.shape
         assert dch == self.display_channels
         self._check(self.L.wf_peak_normalize(self.h, _ptr(data), S, T, row, _ptr(peak), target_db, max_gain, stream))
+
+
+def make_meter_config(settings: dict | None = None, sample_rate: int = 48000, channels: int = 2, max_streams: int = 1,
+                      device: int = -1, mode: int | None = None) -> WfMeterConfig:
+    """Reference setting keys (meter_buf, rms_mode, temporal_smoothing, gravity, fast_peaks, floor;
+    src/settings.hpp:29-135, defaults src/source.cpp:119-174) -> wf_meter_config."""
+    L = load_library()
+    c = WfMeterConfig()
+    L.wf_meter_config_init(C.byref(c))
+    s = dict(settings or {})
+    c.device, c.max_streams, c.sample_rate = device, max_streams, sample_rate
+    c.capture_channels = min(channels, 2)
+    c.meter_ms = int(s.pop("meter_buf", 150))
+    rms = bool(s.pop("rms_mode", True))
+    c.mode = (METER_RMS if rms else METER_PEAK) if mode is None else mode
+    c.tsmoothing = TSMOOTH[s.pop("temporal_smoothing", "exp_moving_avg")]
+    c.gravity = float(s.pop("gravity", 0.65))
+    c.fast_peaks = int(bool(s.pop("fast_peaks", False)))
+    c.floor_db = int(s.pop("floor", -65))
+    if s:
+        raise KeyError(f"unsupported meter settings: {sorted(s)}")
+    return c
+
+
+class MeterEngine:
+    """Level meter (tick_meter) / RMS feed (update_input_rms) on the GPU: ctypes over wf_meter_*; no DSP here."""
+
+    def __init__(self, settings: dict | None = None, sample_rate: int = 48000, channels: int = 2, max_streams: int = 1,
+                 device: int = -1, mode: int | None = None):
+        self.L = load_library()
+        self.cfg = make_meter_config(settings, sample_rate, channels, max_streams, device, mode)
+        h = C.c_void_p()
+        rc = self.L.wf_meter_create(C.byref(self.cfg), C.byref(h))
+        if rc != WF_OK:
+            raise WfError(rc, f"{self.L.wf_strerror(rc).decode()}: {self.L.wf_meter_last_error(None).decode()}")
+        self.h = h
+        self.window = int(self.L.wf_meter_window(self.h))
+
+    def _check(self, rc):
+        if rc != WF_OK:
+            raise WfError(rc, f"{self.L.wf_strerror(rc).decode()}: {self.L.wf_meter_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wf_meter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.wf_meter_launch_count(self.h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.L.wf_meter_last_kernel_ms(self.h))
+
+    def reset(self, first_stream=0, count=None):
+        count = self.cfg.max_streams - first_stream if count is None else count
+        self._check(self.L.wf_meter_reset(self.h, first_stream, count))
+
+    def process(self, pcm, n_ticks: int, hop: int, *, first_stream=0, seconds=1.0 / 60.0, stream=None):
+        """pcm: [n_streams, capture_channels, >= n_ticks*hop] float32, numpy (host) or CUDA torch tensor.
+        Returns dict(db, lin, silent) — or dict(rms=[S, T]) for an INPUT_RMS engine."""
+        is_torch = hasattr(pcm, "data_ptr")
+        if pcm.ndim == 2:
+            pcm = pcm[None]
+        S, cc, ns = pcm.shape
+        if cc != self.cfg.capture_channels:
+            raise ValueError(f"pcm has {cc} channels, meter captures {self.cfg.capture_channels}")
+        if ns < n_ticks * hop:
+            raise ValueError(f"need {n_ticks * hop} samples per channel, got {ns}")
+        if is_torch:
+            import torch
+            assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=pcm.device)
+            f32, u8 = torch.float32, torch.uint8
+        else:
+            pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+            mk = lambda shape, dt: np.empty(shape, dtype=dt)
+            f32, u8 = np.float32, np.uint8
+        feed = self.cfg.mode == METER_INPUT_RMS
+        out = {"rms": mk((S, n_ticks), f32)} if feed else {
+            "db": mk((S, n_ticks, cc), f32), "lin": mk((S, n_ticks, cc), f32), "silent": mk((S, n_ticks), u8)}
+        b = WfMeterBatch()
+        b.struct_size = C.sizeof(WfMeterBatch)
+        b.n_streams, b.n_ticks, b.hop, b.first_stream, b.seconds = S, n_ticks, hop, first_stream, seconds
+        b.pcm, b.stream_stride, b.channel_stride = _ptr(pcm), cc * ns, ns
+        b.out_db = None if feed else _ptr(out["db"])
+        b.out_lin = _ptr(out["rms"]) if feed else _ptr(out["lin"])
+        b.out_silent = None if feed else _ptr(out["silent"])
+        if stream is None:
+            self._check(self.L.wf_meter_process(self.h, C.byref(b)))
+        else:
+            self._check(self.L.wf_meter_process_async(self.h, C.byref(b), 1 if stream == 0 else stream))
+        return out
