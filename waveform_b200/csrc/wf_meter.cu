@@ -48,52 +48,67 @@ struct MParams {
     float floor_m10, db_min;
 };
 
-// sample u of the stream's timeline: history ring first, then this call's PCM
-__device__ __forceinline__ float vsample(const MParams &p, const float *hist_sc, const float *pcm_sc, long long u)
+// Row pointers of one (stream, channel): history ring first (timeline positions [0, W)), then this call's PCM.
+struct Row {
+    const float *hist, *pcm;
+};
+__device__ __forceinline__ Row row_of(const MParams &p, int s, int c)
 {
-    return (u < p.W) ? hist_sc[u] : __ldg(pcm_sc + (u - p.W));
+    return {p.hist + ((size_t)s * p.cc + c) * p.W, p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride};
+}
+__device__ __forceinline__ float vsample(const Row &r, int W, long long u)
+{
+    return (u < W) ? r.hist[u] : __ldg(r.pcm + (u - W));
 }
 
-// the value one sample contributes to partial channel `c`
-__device__ __forceinline__ float contrib(const MParams &p, int s, int c, long long u)
+template<int MODE>
+__device__ __forceinline__ float combine(float a, float b)
 {
-    if(p.mode == WF_METER_INPUT_RMS)
+    return (MODE == WF_METER_PEAK) ? fmaxf(a, b) : __fadd_rn(a, b);
+}
+// what one sample contributes: x^2 (RMS), |x| (peak), (max over channels |x|)^2 (RMS feed, src/source.cpp:1852-1862)
+template<int MODE>
+__device__ __forceinline__ float contrib(float x0, float x1)
+{
+    if(MODE == WF_METER_INPUT_RMS)
     {
-        // (max over channels |x|)^2, src/source.cpp:1852-1862
-        float val = 0.0f;
-        for(int ch = 0; ch < p.cc; ++ch)
-        {
-            const float x = vsample(p, p.hist + ((size_t)s * p.cc + ch) * p.W,
-                                    p.pcm + (size_t)s * p.stream_stride + (size_t)ch * p.channel_stride, u);
-            val = fmaxf(fabsf(x), val);
-        }
-        return __fmul_rn(val, val);
+        const float v = fmaxf(fabsf(x1), fmaxf(fabsf(x0), 0.0f));
+        return __fmul_rn(v, v);
     }
-    const float x = vsample(p, p.hist + ((size_t)s * p.cc + c) * p.W,
-                            p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride, u);
-    return (p.mode == WF_METER_RMS) ? __fmul_rn(x, x) : fabsf(x);
+    return (MODE == WF_METER_RMS) ? __fmul_rn(x0, x0) : fabsf(x0);
 }
-
-__device__ __forceinline__ float combine(int mode, float a, float b)
-{
-    return (mode == WF_METER_PEAK) ? fmaxf(a, b) : __fadd_rn(a, b);
-}
-
-__device__ __forceinline__ float warp_combine(int mode, float v)
+template<int MODE>
+__device__ __forceinline__ float warp_combine(float v)
 {
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1)
-        v = combine(mode, v, __shfl_xor_sync(0xffffffffu, v, o));
+        v = combine<MODE>(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// scalar reduction of timeline positions [lo, hi) by one warp (ragged edges, history, unaligned PCM)
+template<int MODE>
+__device__ __forceinline__ float reduce_range(const Row &r0, const Row &r1, bool two, int W, long long lo, long long hi,
+                                              int lane, float acc)
+{
+    for(long long u = lo + lane; u < hi; u += 32)
+    {
+        const float x0 = vsample(r0, W, u);
+        const float x1 = (MODE == WF_METER_INPUT_RMS && two) ? vsample(r1, W, u) : 0.0f;
+        acc = combine<MODE>(acc, contrib<MODE>(x0, x1));
+    }
+    return acc;
+}
 
-// K1: one warp per (stream, partial channel, block)
-__global__ void meter_block_kernel(const MParams p)
+// K1: one warp per (stream, partial channel, 256-sample block).  Blocks that lie wholly inside 16-byte aligned new PCM
+// (all but the few that touch the history ring or the end) take two 128-bit loads per lane.
+template<int MODE>
+__global__ void meter_block_kernel(const MParams p, const int vec4)
 {
     const int warps_per_cta = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)p.n_streams * p.pc * p.nblk;
     const long long L = (long long)p.W + (long long)p.n_ticks * p.hop;
+    const bool two = (MODE == WF_METER_INPUT_RMS) && p.cc > 1;
     for(long long w = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); w < total;
         w += (long long)gridDim.x * warps_per_cta)
     {
@@ -101,26 +116,41 @@ __global__ void meter_block_kernel(const MParams p)
         const int c = (int)((w / p.nblk) % p.pc);
         const int s = (int)(w / ((long long)p.nblk * p.pc));
         const long long u0 = (long long)j * kBL;
+        const Row r0 = row_of(p, s, c);
+        const Row r1 = two ? row_of(p, s, 1) : r0;
         float acc = 0.0f;
-#pragma unroll
-        for(int k = 0; k < kBL / 32; ++k)
+        if(vec4 && u0 >= p.W && u0 + kBL <= L)
         {
-            const long long u = u0 + lane + 32 * k;
-            if(u < L)
-                acc = combine(p.mode, acc, contrib(p, s, c, u));
+            const float4 *q0 = reinterpret_cast<const float4 *>(r0.pcm + (u0 - p.W)) + lane;
+            const float4 a = __ldg(q0), b = __ldg(q0 + 32);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+            if(two)
+            {
+                const float4 *q1 = reinterpret_cast<const float4 *>(r1.pcm + (u0 - p.W)) + lane;
+                a1 = __ldg(q1);
+                b1 = __ldg(q1 + 32);
+            }
+            acc = combine<MODE>(combine<MODE>(contrib<MODE>(a.x, a1.x), contrib<MODE>(a.y, a1.y)),
+                                combine<MODE>(contrib<MODE>(a.z, a1.z), contrib<MODE>(a.w, a1.w)));
+            acc = combine<MODE>(acc, combine<MODE>(combine<MODE>(contrib<MODE>(b.x, b1.x), contrib<MODE>(b.y, b1.y)),
+                                                   combine<MODE>(contrib<MODE>(b.z, b1.z), contrib<MODE>(b.w, b1.w))));
         }
-        acc = warp_combine(p.mode, acc);
+        else
+            acc = reduce_range<MODE>(r0, r1, two, p.W, u0, min(u0 + kBL, L), lane, acc);
+        acc = warp_combine<MODE>(acc);
         if(lane == 0)
             p.partial[w] = acc;
     }
 }
 
 // K2: one warp per (stream, tick, partial channel): window [lo, hi) of the timeline
+template<int MODE>
 __global__ void meter_window_kernel(const MParams p)
 {
     const int warps_per_cta = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)p.n_streams * p.n_ticks * p.pc;
+    const bool two = (MODE == WF_METER_INPUT_RMS) && p.cc > 1;
     for(long long w = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); w < total;
         w += (long long)gridDim.x * warps_per_cta)
     {
@@ -129,23 +159,20 @@ __global__ void meter_window_kernel(const MParams p)
         const int s = (int)(w / ((long long)p.pc * p.n_ticks));
         const long long lo = (long long)(t + 1) * p.hop, hi = lo + p.W;
         const long long jb = (lo + kBL - 1) / kBL, je = hi / kBL;
+        const Row r0 = row_of(p, s, c);
+        const Row r1 = two ? row_of(p, s, 1) : r0;
         float acc = 0.0f;
         if(jb <= je)
         {
-            for(long long u = lo + lane; u < jb * kBL; u += 32)
-                acc = combine(p.mode, acc, contrib(p, s, c, u));
+            acc = reduce_range<MODE>(r0, r1, two, p.W, lo, jb * kBL, lane, acc);
             const float *part = p.partial + ((size_t)s * p.pc + c) * p.nblk;
             for(long long j = jb + lane; j < je; j += 32)
-                acc = combine(p.mode, acc, part[j]);
-            for(long long u = je * kBL + lane; u < hi; u += 32)
-                acc = combine(p.mode, acc, contrib(p, s, c, u));
+                acc = combine<MODE>(acc, part[j]);
+            acc = reduce_range<MODE>(r0, r1, two, p.W, je * kBL, hi, lane, acc);
         }
         else
-        {
-            for(long long u = lo + lane; u < hi; u += 32)
-                acc = combine(p.mode, acc, contrib(p, s, c, u));
-        }
-        acc = warp_combine(p.mode, acc);
+            acc = reduce_range<MODE>(r0, r1, two, p.W, lo, hi, lane, acc);
+        acc = warp_combine<MODE>(acc);
         if(lane == 0)
             p.raw[w] = acc;
     }
@@ -199,18 +226,21 @@ __global__ void meter_scan_kernel(const MParams p)
     p.flags[s] = last_silent ? 1 : 0;
 }
 
-// K4: ring for the next call = the last W samples of the timeline
+// K4: ring for the next call = the last W samples of the timeline; grid.y = (stream, channel) rows
 __global__ void meter_hist_kernel(const MParams p)
 {
-    const long long total = (long long)p.n_streams * p.cc * p.W;
     const long long shift = (long long)p.n_ticks * p.hop;
-    for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    for(int row = blockIdx.y; row < p.n_streams * p.cc; row += gridDim.y)
     {
-        const int u = (int)(i % p.W);
-        const int c = (int)((i / p.W) % p.cc);
-        const int s = (int)(i / ((long long)p.W * p.cc));
-        p.hist_next[i] = vsample(p, p.hist + ((size_t)s * p.cc + c) * p.W,
-                                 p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride, u + shift);
+        const int s = row / p.cc, c = row % p.cc;
+        const float *hist = p.hist + (size_t)row * p.W;
+        const float *pcm = p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride;
+        float *dst = p.hist_next + (size_t)row * p.W;
+        for(int u = blockIdx.x * blockDim.x + threadIdx.x; u < p.W; u += gridDim.x * blockDim.x)
+        {
+            const long long v = u + shift;
+            dst[u] = (v < p.W) ? hist[v] : __ldg(pcm + (v - p.W));
+        }
     }
 }
 
@@ -547,15 +577,30 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
 
     WFM_CUDA(m, cudaEventRecord(m->ev0, st));
     constexpr int kWarps = 8;
-    meter_block_kernel<<<grid_for((long long)S * pc * nblk, kWarps, m->sm_count), kWarps * 32, 0, st>>>(p);
-    WFM_CUDA(m, cudaGetLastError());
-    meter_window_kernel<<<grid_for((long long)S * T * pc, kWarps, m->sm_count), kWarps * 32, 0, st>>>(p);
+    // 128-bit loads need 16-byte aligned rows (W is a multiple of 16 samples already)
+    const int vec4 = (((uintptr_t)d_pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->channel_stride & 3) == 0);
+    const int g1 = grid_for((long long)S * pc * nblk, kWarps, m->sm_count), g2 = grid_for((long long)S * T * pc, kWarps, m->sm_count);
+    switch(m->cfg.mode)
+    {
+    case WF_METER_PEAK:
+        meter_block_kernel<WF_METER_PEAK><<<g1, kWarps * 32, 0, st>>>(p, vec4);
+        meter_window_kernel<WF_METER_PEAK><<<g2, kWarps * 32, 0, st>>>(p);
+        break;
+    case WF_METER_RMS:
+        meter_block_kernel<WF_METER_RMS><<<g1, kWarps * 32, 0, st>>>(p, vec4);
+        meter_window_kernel<WF_METER_RMS><<<g2, kWarps * 32, 0, st>>>(p);
+        break;
+    default:
+        meter_block_kernel<WF_METER_INPUT_RMS><<<g1, kWarps * 32, 0, st>>>(p, vec4);
+        meter_window_kernel<WF_METER_INPUT_RMS><<<g2, kWarps * 32, 0, st>>>(p);
+        break;
+    }
     WFM_CUDA(m, cudaGetLastError());
     meter_scan_kernel<<<(int)((S + 127) / 128), 128, 0, st>>>(p);
     WFM_CUDA(m, cudaGetLastError());
     {
-        const long long total = (long long)S * cc * W;
-        meter_hist_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)m->sm_count * 16), 256, 0, st>>>(p);
+        const dim3 hg((unsigned)std::min((W + 255) / 256, 64), (unsigned)std::min<size_t>(S * cc, 65535));
+        meter_hist_kernel<<<hg, 256, 0, st>>>(p);
         WFM_CUDA(m, cudaGetLastError());
     }
     m->launches += 4;

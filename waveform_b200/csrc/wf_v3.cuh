@@ -1,4 +1,4 @@
-// wf_v3.cuh — the fused spectrum pipeline for fft sizes 4096 / 8192 / 16384: one CTA per tick, a cluster of R CTAs
+// wf_v3.cuh — the fused spectrum pipeline for fft sizes 1024 ... 16384 (powers of two): one CTA per tick, a cluster of R CTAs
 // (R = 1, 2, 4, 8) per stream, and a three-pass register FFT whose every shared-memory access is base + immediate.
 //
 // ncu on the first-generation kernels (profiles/r01i_generic8192.txt) showed 16 750 warp-instructions per N=8192 frame,
@@ -28,6 +28,8 @@ namespace wf {
 namespace v3 {
 
 template<int N> struct Plan3;
+template<> struct Plan3<1024> { static constexpr int A = 8, B = 8, C = 8; };
+template<> struct Plan3<2048> { static constexpr int A = 16, B = 8, C = 8; };
 template<> struct Plan3<4096> { static constexpr int A = 16, B = 16, C = 8; };
 template<> struct Plan3<8192> { static constexpr int A = 16, B = 16, C = 16; };
 template<> struct Plan3<16384> { static constexpr int A = 32, B = 16, C = 16; };
@@ -48,7 +50,8 @@ struct Geo3 {
     static constexpr int L1_ELEMS = A * S1;
     static constexpr int L2_ELEMS = B * SB;
     static constexpr int BUF = (L1_ELEMS > L2_ELEMS ? L1_ELEMS : L2_ELEMS); // one buffer serves L1, L2, X and the inbox
-    static constexpr int MINB = (512 / TN) > 0 ? (512 / TN) : 1;
+    static constexpr int TPSM = (P <= 8) ? 1024 : 512; // resident threads per SM the register cap allows (64 / 128 registers)
+    static constexpr int MINB = (TPSM / TN) > 0 ? (TPSM / TN) : 1;
 };
 
 struct Tw3 {
@@ -88,6 +91,12 @@ struct Fft3 {
             for(int a = 0; a < A; ++a)
                 v[a] = make_float2(ldg_stream_f1(f1 + 2 * a * TN), ldg_stream_f1(f1 + 2 * a * TN + 1));
         }
+    }
+    // pull a frame's cache lines into L2 (when there is no register room for a register prefetch)
+    static __device__ __forceinline__ void prefetch_l2(const float *frame, int tid)
+    {
+        for(int l = tid; l < N / 32; l += TN)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(frame + l * 32));
     }
     // non-zero test (src/source_generic.cpp:63-76) + window multiply (:97-103); returns "any sample non-zero" (this thread)
     static __device__ __forceinline__ bool finish_load(pk::c64 (&x)[P], const float2 (&v)[P], const float2 *window2, int tid)
@@ -261,17 +270,6 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
     float *hold_s = p.hold_db + (size_t)s * och * B;
 
-    auto cl_arrive = [&]() {
-        if constexpr(R > 1)
-            cluster_arrive();
-    };
-    auto cl_wait = [&]() {
-        if constexpr(R > 1)
-            cluster_wait();
-        else
-            __syncthreads();
-    };
-
     // cluster-wide AND of the per-thread partial "outputs <= floor-10" flags of the last tick that produced outputs
     auto ensure_po_valid = [&]() {
         if(po_valid)
@@ -302,6 +300,209 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         po_valid = true;
     };
 
+    // ---- pieces shared by the R == 1 and R > 1 flows -------------------------------------------------------------
+    // gate of one capture channel for one tick, src/source_generic.cpp:63-95; returns "this channel is processed"
+    auto gate_channel = [&](int c, bool nz_c, bool skip_all, const bool (&proc)[2], unsigned &silent_channels) -> bool {
+        bool do_proc = !skip_all;
+        if(!skip_all)
+        {
+            const bool silent = !nz_c;
+            if(!silent)
+                last_silent = false;
+            if(silent && p.gate)
+            {
+                if(last_silent)
+                    do_proc = false;
+                else
+                {
+                    bool outsilent;
+                    if(!stereo && c == 1 && proc[0])
+                        outsilent = false; // slot 0 holds channel 0's fresh linear magnitudes
+                    else
+                    {
+                        ensure_po_valid();
+                        outsilent = (stereo && c == 1) ? po1 : po0;
+                    }
+                    if(outsilent)
+                    {
+                        if(++silent_channels >= (unsigned)CC)
+                            last_silent = true;
+                        do_proc = false;
+                    }
+                }
+            }
+        }
+        return do_proc;
+    };
+    // EMA of one bin, src/source_generic.cpp:124-132
+    auto ema = [&](float mag, float &state, bool do_proc) {
+        if(p.tsmooth)
+        {
+            float oldval = state;
+            if(EXTRA && p.fast_peaks)
+                oldval = fmaxf(mag, oldval);
+            mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+        }
+        if(do_proc)
+            state = mag;
+    };
+    // split pass of pair j of my tick -> (|X[k1]|, |X[k2]|), normalised, slope applied (src/source_generic.cpp:110-122)
+    auto split_pair = [&](const pk::c64 *X, const pk::c64 *twp, int j, float &m1, float &m2) {
+        const int k1 = tid + j * TN;
+        const pk::c64 a = X[k1];
+        // X[M - k1]: descending addresses (conflict free); thread 0 pairs bin 0 with itself
+        const pk::c64 bq = X[(j == 0 && tid == 0) ? 0 : (M - k1)];
+        const pk::c64 b = pk::conj(bq);
+        const pk::c64 sum = pk::add(a, b);
+        const pk::c64 o = pk::mul_neg_i(pk::sub(a, b));
+        const pk::c64 wo = pk::cmul(o, __ldg(twp + j * TN));
+        const pk::c64 y1 = pk::add(sum, wo);
+        const pk::c64 y2 = pk::sub(sum, wo);
+        const pk::c64 s1 = pk::mul(y1, y1), s2 = pk::mul(y2, y2);
+        float p1 = pk::re(s1) + pk::im(s1);
+        float p2 = pk::re(s2) + pk::im(s2);
+        if(j == 0)
+        {
+            // thread 0: second slot = bin M/2, whose split pass is 2*conj(X[M/2])
+            const pk::c64 xm = X[M / 2];
+            const pk::c64 sq = pk::mul(xm, xm);
+            const float pm = 4.0f * (pk::re(sq) + pk::im(sq));
+            p2 = (tid == 0) ? pm : p2;
+        }
+        pk::c64 m = pk::mul(pk::make(sqrt_mufu(p1), sqrt_mufu(p2)), pk::make(p.coef_half, p.coef_half));
+        if(EXTRA && p.slope != nullptr)
+            m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + ((j == 0) ? k2_first : k2_base - j * TN))));
+        pk::split(m, m1, m2);
+    };
+    // outputs of one tick from the state registers, src/source_generic.cpp:136-179
+    auto do_outputs = [&](int t, int f, const bool (&proc)[2]) {
+        const float *prev_db = (p.out_db != nullptr && t > 0) ? p.out_db + ((size_t)s * T + (t - 1)) * dch * B : hold_s;
+        float vc = 0.0f;
+        if(EXTRA && p.normalize)
+        {
+            const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + t] : 0.0f;
+            vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
+        }
+        float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * T + t) * dch * B : nullptr;
+        uint32_t gather_sa = 0u;
+        if(R > 1 && want_points)
+            gather_sa = mapa(dbfull_sa, (unsigned)f);
+        float peak = -INFINITY;
+        bool outs0 = true, outs1 = true;
+        auto emit = [&](int d, int k, float outv, bool &outs) {
+            outs &= !(outv > p.floor_m10);
+            if(EXTRA && k >= 1)
+                peak = fmaxf(peak, outv);
+            if(odb != nullptr)
+                stg_stream(odb + d * B + k, outv);
+            if(mirror_each_frame)
+                hold_s[d * B + k] = outv;
+            if(want_points)
+            {
+                if constexpr(R > 1)
+                    st_cluster_f32(gather_sa + (uint32_t)((d * B + k) * sizeof(float)), outv);
+                else
+                    dbfull[d * B + k] = outv;
+            }
+        };
+        auto finish = [&](float in, int k) -> float {
+            float outv = dbfs_mufu(in, p.db_min);
+            if(EXTRA && k >= 1)
+            {
+                if(p.normalize)
+                    outv += vc; // :161-167
+                if(p.rolloff != nullptr)
+                    outv = fmaxf(outv - __ldg(p.rolloff + k), p.db_min); // :169-179
+            }
+            return outv;
+        };
+        const bool all_proc = proc[0] && (CC == 1 || proc[1]);
+        if(!last_silent && all_proc)
+        {
+            // hot path: every channel processed this tick — straight-line code
+            for(int d = 0; d < dch; ++d)
+            {
+                bool outs = true;
+#pragma unroll
+                for(int i = 0; i < NST; ++i)
+                {
+                    float in;
+                    if(CC == 2 && !stereo)
+                        in = (st[0][i] + st[CC - 1][i]) * 0.5f; // :150-154
+                    else
+                        in = (CC == 2 && d == 1) ? st[CC - 1][i] : st[0][i];
+                    const int k = bin_of(i);
+                    emit(d, k, finish(in, k), outs);
+                }
+                if(d == 0)
+                    outs0 = outs;
+                else
+                    outs1 = outs;
+            }
+        }
+        else
+        {
+            // rare paths: tick returned early (hold, :138-139) or a channel was skipped (stale dB re-converted)
+            for(int d = 0; d < dch; ++d)
+            {
+                bool outs = true;
+#pragma unroll 1
+                for(int i = 0; i < NST; ++i)
+                {
+                    const int k = bin_of(i);
+                    float s0 = 0.0f, s1 = 0.0f; // st[.][i] with a run-time i: select, no local-memory indexing
+#pragma unroll
+                    for(int ii = 0; ii < NST; ++ii)
+                        if(ii == i)
+                        {
+                            s0 = st[0][ii];
+                            s1 = st[CC - 1][ii];
+                        }
+                    float outv;
+                    if(last_silent)
+                        outv = prev_db[d * B + k];
+                    else
+                    {
+                        float in;
+                        if(CC == 2 && !stereo)
+                        {
+                            const float in0 = proc[0] ? s0 : prev_db[k];
+                            in = (in0 + s1) * 0.5f;
+                        }
+                        else
+                        {
+                            const int c = (CC == 2) ? d : 0;
+                            in = proc[c] ? ((c == 0) ? s0 : s1) : prev_db[c * B + k];
+                        }
+                        outv = finish(in, k);
+                    }
+                    emit(d, k, outv, outs);
+                }
+                if(d == 0)
+                    outs0 = outs;
+                else
+                    outs1 = outs;
+            }
+        }
+        if(!last_silent && p.gate)
+        {
+            part0 = outs0;
+            part1 = outs1;
+            po_valid = false;
+        }
+        if(p.out_silent != nullptr && r == 0 && tid == 0)
+            p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
+        if(EXTRA && p.out_peak != nullptr)
+        {
+            const float gm = group_max<TN>(peak, red_scratch);
+            if(tid == 0)
+                atomic_max_float(p.out_peak + t, gm);
+        }
+    };
+
+    // PCM prefetch: with 16 points per thread the NEXT frame's samples are requested as soon as the current ones have
+    // been windowed (in flight during the whole FFT); with 32 there is no register room until the split pass is over.
+    constexpr bool EARLY_PF = (P <= 16) && (CC == 1); // two capture channels: no register room either -> L2 prefetch
     float2 v[P];
     if((int)r < T)
         F::load_raw(v, pcm_s + (size_t)r * p.hop, p.aligned8, tid);
@@ -310,61 +511,88 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     {
         const int nf = min(R, T - t0);
         const bool mine = (int)r < nf;
-        float magr[CC][P]; // [c][2*j] = |X[k1]|, [c][2*j+1] = |X[k2]| (normalised, slope applied)
-        unsigned nzbits = 0;
+        const int my_t = t0 + (int)r;
+        // next frame this CTA will need after (my tick, channel c)
+        auto next_frame = [&](int c) -> const float * {
+            if(c + 1 < CC)
+                return pcm_s + (size_t)(c + 1) * p.channel_stride + (size_t)my_t * p.hop;
+            return (my_t + R < T) ? pcm_s + (size_t)(my_t + R) * p.hop : nullptr;
+        };
 
-        // ---- phase 1: window, FFT, split pass, magnitude of my tick (src/source_generic.cpp:97-122) ----
-        if(mine)
+        if constexpr(R == 1)
         {
+            // ---- one CTA per stream: FFT -> gate -> split pass -> EMA per channel, all in registers ----
+            const int t = t0;
+            const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
+            bool proc[2] = {false, false};
+            unsigned silent_channels = 0;
 #pragma unroll
             for(int c = 0; c < CC; ++c)
             {
-                if(c > 0)
-                    F::load_raw(v, pcm_s + (size_t)c * p.channel_stride + (size_t)(t0 + r) * p.hop, p.aligned8, tid);
                 pk::c64 x[P];
                 const bool nzt = F::finish_load(x, v, p.window2, tid);
+                const float *nx = next_frame(c);
+                if(nx != nullptr)
+                {
+                    if(EARLY_PF)
+                        F::load_raw(v, nx, p.aligned8, tid);
+                    else
+                        F::prefetch_l2(nx, tid);
+                }
                 const bool nz = F::run(x, buf, tw, tid, nzt);
-                nzbits |= nz ? (1u << c) : 0u;
+                if(!EARLY_PF && nx != nullptr)
+                    F::load_raw(v, nx, p.aligned8, tid);
+                const bool do_proc = gate_channel(c, nz, skip_all, proc, silent_channels);
+                proc[c] = do_proc;
                 const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);
                 const pk::c64 *twp = reinterpret_cast<const pk::c64 *>(p.tw_post) + tid;
-                const pk::c64 ch2 = pk::make(p.coef_half, p.coef_half);
 #pragma unroll
                 for(int j = 0; j < HP; ++j)
                 {
-                    const int k1 = tid + j * TN;
-                    const pk::c64 a = X[k1];
-                    // X[M - k1]: descending addresses (conflict free); thread 0 pairs bin 0 with itself
-                    const pk::c64 bq = X[(j == 0 && tid == 0) ? 0 : (M - k1)];
-                    const pk::c64 b = pk::conj(bq);
-                    const pk::c64 sum = pk::add(a, b);
-                    const pk::c64 o = pk::mul_neg_i(pk::sub(a, b));
-                    const pk::c64 wo = pk::cmul(o, __ldg(twp + j * TN));
-                    const pk::c64 y1 = pk::add(sum, wo);
-                    const pk::c64 y2 = pk::sub(sum, wo);
-                    const pk::c64 s1 = pk::mul(y1, y1), s2 = pk::mul(y2, y2);
-                    float p1 = pk::re(s1) + pk::im(s1);
-                    float p2 = pk::re(s2) + pk::im(s2);
-                    if(j == 0)
-                    {
-                        // thread 0: second slot = bin M/2, whose split pass is 2*conj(X[M/2])
-                        const pk::c64 xm = X[M / 2];
-                        const pk::c64 sq = pk::mul(xm, xm);
-                        const float pm = 4.0f * (pk::re(sq) + pk::im(sq));
-                        p2 = (tid == 0) ? pm : p2;
-                    }
-                    pk::c64 m = pk::mul(pk::make(sqrt_mufu(p1), sqrt_mufu(p2)), ch2);
-                    if(EXTRA && p.slope != nullptr)
-                    {
-                        const int k2 = (k1 == 0) ? M / 2 : M - k1;
-                        m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + k2)));
-                    }
-                    pk::split(m, magr[c][2 * j], magr[c][2 * j + 1]);
+                    float m1, m2;
+                    split_pair(X, twp, j, m1, m2);
+                    ema(m1, st[c][2 * j], do_proc);
+                    ema(m2, st[c][2 * j + 1], do_proc);
                 }
             }
+            do_outputs(t, 0, proc);
+            if(want_points)
+            {
+                __syncthreads();
+                display_stage<TN>(p, dbfull, pts, B, dch, (size_t)s * T + t, tid, true, red_scratch);
+            }
         }
-
-        if constexpr(R > 1)
+        else
         {
+            float magr[CC][P]; // [c][2*j] = |X[k1]|, [c][2*j+1] = |X[k2]|
+            unsigned nzbits = 0;
+            // ---- phase 1: window, FFT, split pass, magnitude of my tick (src/source_generic.cpp:97-122) ----
+            if(mine)
+            {
+#pragma unroll
+                for(int c = 0; c < CC; ++c)
+                {
+                    pk::c64 x[P];
+                    const bool nzt = F::finish_load(x, v, p.window2, tid);
+                    const float *nx = next_frame(c);
+                    if(nx != nullptr)
+                    {
+                        if(EARLY_PF)
+                            F::load_raw(v, nx, p.aligned8, tid);
+                        else
+                            F::prefetch_l2(nx, tid);
+                    }
+                    const bool nz = F::run(x, buf, tw, tid, nzt);
+                    if(!EARLY_PF && c + 1 < CC)
+                        F::load_raw(v, nx, p.aligned8, tid); // the other channel of my tick
+                    nzbits |= nz ? (1u << c) : 0u;
+                    const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);
+                    const pk::c64 *twp = reinterpret_cast<const pk::c64 *>(p.tw_post) + tid;
+#pragma unroll
+                    for(int j = 0; j < HP; ++j)
+                        split_pair(X, twp, j, magr[c][2 * j], magr[c][2 * j + 1]);
+                }
+            }
             __syncthreads(); // my FFT buffer is free: it becomes the inbox
             cluster_arrive(); // barrier A
             cluster_wait();
@@ -390,217 +618,37 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                     st_cluster_u32(mapa(smem_u32(&nzf[r]), (unsigned)tid), nzbits);
             }
             cluster_arrive(); // barrier B
-            if(t0 + R + (int)r < T)
-                F::load_raw(v, pcm_s + (size_t)(t0 + R + r) * p.hop, p.aligned8, tid);
+            if(!EARLY_PF && mine && my_t + R < T)
+                F::load_raw(v, pcm_s + (size_t)(my_t + R) * p.hop, p.aligned8, tid);
             cluster_wait();
-        }
-        else
-        {
-            if(tid == 0)
-                nzf[0] = nzbits;
-            if(t0 + 1 < T)
-                F::load_raw(v, pcm_s + (size_t)(t0 + 1) * p.hop, p.aligned8, tid);
-            __syncthreads();
-        }
 
-        // ---- phase 3: my bins through the round's ticks, in order ----
-        for(int f = 0; f < nf; ++f)
-        {
-            const int t = t0 + f;
-            const unsigned nzb = nzf[f];
-            const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
-            bool proc[2] = {false, false};
-            unsigned silent_channels = 0;
-            const float *prev_db =
-                (p.out_db != nullptr && t > 0) ? p.out_db + ((size_t)s * T + (t - 1)) * dch * B : hold_s;
-
+            // ---- phase 3: my bins through the round's ticks, in order ----
+            for(int f = 0; f < nf; ++f)
+            {
+                const int t = t0 + f;
+                const unsigned nzb = nzf[f];
+                const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
+                bool proc[2] = {false, false};
+                unsigned silent_channels = 0;
 #pragma unroll
-            for(int c = 0; c < CC; ++c)
-            {
-                // gate, src/source_generic.cpp:63-95
-                bool do_proc = !skip_all;
-                if(!skip_all)
+                for(int c = 0; c < CC; ++c)
                 {
-                    const bool silent = ((nzb >> c) & 1u) == 0;
-                    if(!silent)
-                        last_silent = false;
-                    if(silent && p.gate)
-                    {
-                        if(last_silent)
-                            do_proc = false;
-                        else
-                        {
-                            bool outsilent;
-                            if(!stereo && c == 1 && proc[0])
-                                outsilent = false;
-                            else
-                            {
-                                ensure_po_valid();
-                                outsilent = (stereo && c == 1) ? po1 : po0;
-                            }
-                            if(outsilent)
-                            {
-                                if(++silent_channels >= (unsigned)CC)
-                                    last_silent = true;
-                                do_proc = false;
-                            }
-                        }
-                    }
-                }
-                proc[c] = do_proc;
-                // EMA, src/source_generic.cpp:124-132
-#pragma unroll
-                for(int i = 0; i < NST; ++i)
-                {
-                    float mag;
-                    if constexpr(R == 1)
-                        mag = magr[c][i];
-                    else
-                        mag = inbox[(f * CC + c) * SLICE + tid + i * TN];
-                    if(p.tsmooth)
-                    {
-                        float oldval = st[c][i];
-                        if(EXTRA && p.fast_peaks)
-                            oldval = fmaxf(mag, oldval);
-                        mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
-                    }
-                    if(do_proc)
-                        st[c][i] = mag;
-                }
-            }
-
-            // ---- outputs, src/source_generic.cpp:136-179 ----
-            float vc = 0.0f;
-            if(EXTRA && p.normalize)
-            {
-                const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + t] : 0.0f;
-                vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
-            }
-            float *odb = (p.out_db != nullptr) ? p.out_db + ((size_t)s * T + t) * dch * B : nullptr;
-            uint32_t gather_sa = 0u;
-            if(R > 1 && want_points)
-                gather_sa = mapa(dbfull_sa, (unsigned)f);
-            float peak = -INFINITY;
-            bool outs0 = true, outs1 = true;
-            // one output value: common tail of both paths below
-            auto emit = [&](int d, int k, float outv, bool &outs) {
-                outs &= !(outv > p.floor_m10);
-                if(EXTRA && k >= 1)
-                    peak = fmaxf(peak, outv);
-                if(odb != nullptr)
-                    stg_stream(odb + d * B + k, outv);
-                if(mirror_each_frame)
-                    hold_s[d * B + k] = outv;
-                if(want_points)
-                {
-                    if constexpr(R > 1)
-                        st_cluster_f32(gather_sa + (uint32_t)((d * B + k) * sizeof(float)), outv);
-                    else
-                        dbfull[d * B + k] = outv;
-                }
-            };
-            auto finish = [&](float in, int k) -> float {
-                float outv = dbfs_mufu(in, p.db_min);
-                if(EXTRA && k >= 1)
-                {
-                    if(p.normalize)
-                        outv += vc; // :161-167
-                    if(p.rolloff != nullptr)
-                        outv = fmaxf(outv - __ldg(p.rolloff + k), p.db_min); // :169-179
-                }
-                return outv;
-            };
-            const bool all_proc = proc[0] && (CC == 1 || proc[1]);
-            if(!last_silent && all_proc)
-            {
-                // ---- hot path: every channel processed this tick — straight-line code ----
-                for(int d = 0; d < dch; ++d)
-                {
-                    bool outs = true;
+                    const bool do_proc = gate_channel(c, ((nzb >> c) & 1u) != 0, skip_all, proc, silent_channels);
+                    proc[c] = do_proc;
 #pragma unroll
                     for(int i = 0; i < NST; ++i)
-                    {
-                        float in;
-                        if(CC == 2 && !stereo)
-                            in = (st[0][i] + st[CC - 1][i]) * 0.5f; // :150-154
-                        else
-                            in = (CC == 2 && d == 1) ? st[CC - 1][i] : st[0][i];
-                        const int k = bin_of(i);
-                        emit(d, k, finish(in, k), outs);
-                    }
-                    if(d == 0)
-                        outs0 = outs;
-                    else
-                        outs1 = outs;
+                        ema(inbox[(f * CC + c) * SLICE + tid + i * TN], st[c][i], do_proc);
                 }
+                do_outputs(t, f, proc);
             }
-            else
+            // ---- phase 4: render-time stages of my tick from the gathered dB spectrum ----
+            if(want_points)
             {
-                // ---- rare paths: tick returned early (hold, :138-139) or a channel was skipped (stale dB re-converted) ----
-                for(int d = 0; d < dch; ++d)
-                {
-                    bool outs = true;
-#pragma unroll 1
-                    for(int i = 0; i < NST; ++i)
-                    {
-                        const int k = bin_of(i);
-                        float s0 = 0.0f, s1 = 0.0f; // st[.][i] with a run-time i: select without local-memory indexing
-#pragma unroll
-                        for(int ii = 0; ii < NST; ++ii)
-                            if(ii == i)
-                            {
-                                s0 = st[0][ii];
-                                s1 = st[CC - 1][ii];
-                            }
-                        float outv;
-                        if(last_silent)
-                            outv = prev_db[d * B + k];
-                        else
-                        {
-                            float in;
-                            if(CC == 2 && !stereo)
-                            {
-                                const float in0 = proc[0] ? s0 : prev_db[k];
-                                in = (in0 + s1) * 0.5f;
-                            }
-                            else
-                            {
-                                const int c = (CC == 2) ? d : 0;
-                                in = proc[c] ? ((c == 0) ? s0 : s1) : prev_db[c * B + k];
-                            }
-                            outv = finish(in, k);
-                        }
-                        emit(d, k, outv, outs);
-                    }
-                    if(d == 0)
-                        outs0 = outs;
-                    else
-                        outs1 = outs;
-                }
+                cluster_arrive(); // barrier C
+                cluster_wait();
+                if(mine)
+                    display_stage<TN>(p, dbfull, pts, B, dch, (size_t)s * T + my_t, tid, true, red_scratch);
             }
-            if(!last_silent && p.gate)
-            {
-                part0 = outs0;
-                part1 = outs1;
-                po_valid = false;
-            }
-            if(p.out_silent != nullptr && r == 0 && tid == 0)
-                p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
-            if(EXTRA && p.out_peak != nullptr)
-            {
-                const float gm = group_max<TN>(peak, red_scratch);
-                if(tid == 0)
-                    atomic_max_float(p.out_peak + t, gm);
-            }
-        }
-
-        // ---- phase 4: render-time stages of my tick from the gathered dB spectrum ----
-        if(want_points)
-        {
-            cl_arrive(); // barrier C
-            cl_wait();
-            if(mine)
-                display_stage<TN>(p, dbfull, pts, B, dch, (size_t)s * T + t0 + r, tid, true, red_scratch);
         }
         // (the next round's FFT starts with a block barrier before it overwrites the buffer)
     }

@@ -9,13 +9,15 @@ namespace wf {
 cudaError_t v3_launch_c2(int N, int R, bool extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display,
                          int device);
 
-bool v3_supported(int N) { return N == 4096 || N == 8192 || N == 16384; }
+bool v3_supported(int N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384; }
 int v3_min_cluster(int N) { return (N <= 8192) ? 1 : 2; }
 
 size_t v3_smem_bytes(int N, int dch, int n_points, bool display)
 {
     switch(N)
     {
+    case 1024: return v3::smem_bytes<1024>(dch, n_points, display);
+    case 2048: return v3::smem_bytes<2048>(dch, n_points, display);
     case 4096: return v3::smem_bytes<4096>(dch, n_points, display);
     case 8192: return v3::smem_bytes<8192>(dch, n_points, display);
     case 16384: return v3::smem_bytes<16384>(dch, n_points, display);
@@ -49,6 +51,8 @@ void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2)
 {
     switch(N)
     {
+    case 1024: build_tw<1024>(tw1, tw2); break;
+    case 2048: build_tw<2048>(tw1, tw2); break;
     case 4096: build_tw<4096>(tw1, tw2); break;
     case 8192: build_tw<8192>(tw1, tw2); break;
     case 16384: build_tw<16384>(tw1, tw2); break;

@@ -59,6 +59,12 @@ cudaError_t launch_cc(int N, int R, bool extra, const KParams &kp, const v3::Tw3
 {
     switch(N)
     {
+    case 1024:
+        return extra ? launch_r<1024, CC, true>(R, kp, tw, st, display, device)
+                     : launch_r<1024, CC, false>(R, kp, tw, st, display, device);
+    case 2048:
+        return extra ? launch_r<2048, CC, true>(R, kp, tw, st, display, device)
+                     : launch_r<2048, CC, false>(R, kp, tw, st, display, device);
     case 4096:
         return extra ? launch_r<4096, CC, true>(R, kp, tw, st, display, device)
                      : launch_r<4096, CC, false>(R, kp, tw, st, display, device);
