@@ -213,7 +213,7 @@ int pick_wide_r(const wf_engine *e, const KParams &kp, bool display)
     const int N = e->tab.N;
     if(!wide_supported(N) || e->wide_r == 1)
         return 1;
-    if(wide_smem_bytes(N, kp.dch, kp.n_points, display) > 227 * 1024)
+    if(wide_smem_bytes(N, kp.dch, kp.scratch_q, display) > 227 * 1024)
         return 1;
     if(e->wide_r == 2 || e->wide_r == 4 || e->wide_r == 8)
         return e->wide_r;
@@ -241,7 +241,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
 {
     {
         const bool display = kp.out_points || kp.out_pixels || kp.out_min;
-        if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.n_points, display) <= 227 * 1024)
+        if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.scratch_q, display) <= 227 * 1024)
         {
             const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
             WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, st, display, e->device));
@@ -812,6 +812,8 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     kp.band_widths = e->d_band_widths;
     kp.band_offsets = e->d_band_offsets;
     kp.n_points = t.num_points;
+    kp.n_sample = (t.cfg.display_mode == WF_DISPLAY_BAR && t.cfg.interp_mode != WF_INTERP_POINT) ? (int)t.interp_indices.size() : 0;
+    kp.scratch_q = t.num_points + (dch * kp.n_sample + 3) / 4;
     kp.taps = t.interp_taps;
     kp.radius = t.interp_radius;
     kp.display_bar = (t.cfg.display_mode == WF_DISPLAY_BAR);
@@ -844,7 +846,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         case 2048: groups = Geo<2048>::GROUPS; break;
         default: groups = 1; break;
         }
-        extra = (size_t)groups * 4 * (size_t)t.num_points * sizeof(float);
+        extra = (size_t)groups * 4 * (size_t)kp.scratch_q * sizeof(float);
     }
     const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
     const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&

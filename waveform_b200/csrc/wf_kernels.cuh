@@ -63,6 +63,8 @@ struct KParams {
     const int *band_widths;
     const int *band_offsets;
     int n_points, taps, radius, display_bar, interp_mode;
+    int n_sample;   // bars with a Lanczos / Catmull-Rom kernel: sample points of all bands (sum of band_widths), else 0
+    int scratch_q;  // display scratch per stream = 4 * scratch_q floats (>= 4*n_points + dch*n_sample)
     const float *gauss_w;
     int gauss_radius, gauss_size;
     float gauss_sum;
@@ -368,11 +370,42 @@ struct Fft<N, PlanT<TN_, R0, Rest...>> {
     }
 };
 
-// kernel_convolve, src/filter.hpp:160-169 (sequential mul+add, no contraction)
+// kernel_convolve, src/filter.hpp:160-169 (sequential mul+add, no contraction).  Away from the spectrum's edges the
+// window is complete: all taps' weights (one or two 128-bit loads) and samples are fetched first, then accumulated in
+// the reference's order — same rounding, no load latency inside the dependent chain.
+template<int TAPS>
+__device__ __forceinline__ float kernel_convolve_full(const float *db, const float *__restrict__ w)
+{
+    float wt[TAPS], x[TAPS];
+#pragma unroll
+    for(int q = 0; q < TAPS / 4; ++q)
+    {
+        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(w) + q);
+        wt[4 * q] = w4.x;
+        wt[4 * q + 1] = w4.y;
+        wt[4 * q + 2] = w4.z;
+        wt[4 * q + 3] = w4.w;
+    }
+#pragma unroll
+    for(int i = 0; i < TAPS; ++i)
+        x[i] = db[i];
+    float sum = 0.0f;
+#pragma unroll
+    for(int i = 0; i < TAPS; ++i)
+        sum = __fadd_rn(sum, __fmul_rn(x[i], wt[i]));
+    return sum;
+}
 __device__ __forceinline__ float kernel_convolve(const float *db, int sz, const float *__restrict__ w, int radius, int index)
 {
     const int start = (index - radius) + 1;
     const int stop = min(index + radius + 1, sz);
+    if(start >= 0 && index + radius + 1 <= sz)
+    {
+        if(radius == 4)
+            return kernel_convolve_full<8>(db + start, w); // Lanczos a = 4
+        if(radius == 2)
+            return kernel_convolve_full<4>(db + start, w); // Catmull-Rom
+    }
     float sum = 0.0f;
     for(int i = max(start, 0); i < stop; ++i)
         sum = __fadd_rn(sum, __fmul_rn(db[i], __ldg(w + (i - start))));
@@ -448,7 +481,7 @@ __device__ __forceinline__ float std_lerp_dev(float a, float b, float t)
 //   -> Gaussian smoothing (src/filter.hpp:133-180) -> out_points
 //   -> dB -> pixel height (lerp/clamp), running (miny, minpos), frequency-axis mirroring
 //      (src/source.cpp:1408-1424 curve, :1548-1565 bars) -> out_pixels / out_min
-// `pts` is scratch for [2][dch][n_points] floats.  TN threads (one group) cooperate; SYNC() is the group barrier.
+// `pts` is scratch for [2][dch][n_points] (+ [dch][n_sample]) floats: 4 * scratch_q floats per stream.  TN threads (one group) cooperate; SYNC() is the group barrier.
 template<int TN>
 __device__ __forceinline__ void display_stage(const KParams &p, const float *dbs, float *pts, int B, int dch, size_t tick,
                                               int tid, bool active, float *red)
@@ -457,12 +490,36 @@ __device__ __forceinline__ void display_stage(const KParams &p, const float *dbs
     const bool need_smem = p.filter || (p.out_pixels != nullptr) || (p.out_min != nullptr);
     float *raw = pts;                 // interpolated points
     float *fin = pts + dch * np;      // after the Gaussian (or alias of raw)
+    // Bars with an interpolation kernel: a bar is the mean of band_width kernel sums (src/filter.hpp:195-211) and the
+    // high-frequency bars are wide, so one thread per bar would leave the group waiting for the widest bar.  Phase A
+    // evaluates every sample point of every band in parallel; phase B adds them per bar in the reference's order.
+    const bool two_phase = p.display_bar && p.interp_mode != 0 && p.n_sample > 0;
+    float *tmp = pts + 4 * np;        // [dch][n_sample]
+    if(two_phase)
+    {
+        for(int d = 0; d < dch; ++d)
+            for(int q = tid; q < p.n_sample; q += TN)
+                tmp[d * p.n_sample + q] =
+                    kernel_convolve(dbs + d * B, B, p.interp_w + (size_t)q * p.taps, p.radius, (int)__ldg(p.interp_idx + q));
+        group_sync<TN>();
+    }
     for(int d = 0; d < dch; ++d)
     {
         const float *db = dbs + d * B;
         for(int i = tid; i < np; i += TN)
         {
-            const float val = interp_point(p, db, B, i);
+            float val;
+            if(two_phase)
+            {
+                const int count = __ldg(p.band_widths + i);
+                const float *src = tmp + d * p.n_sample + __ldg(p.band_offsets + i);
+                float sum = 0.0f;
+                for(int j = 0; j < count; ++j)
+                    sum = __fadd_rn(sum, src[j]);
+                val = __fdiv_rn(sum, (float)count);
+            }
+            else
+                val = interp_point(p, db, B, i);
             if(need_smem)
                 raw[d * np + i] = val;
             else if(active)
@@ -561,7 +618,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA, Geo<N>::MINB) stft_fused_kernel(c
     const int tid = threadIdx.x % TN;
     float2 *buf = smem + (size_t)grp * G::BUF;
     float *dbs = reinterpret_cast<float *>(buf); // dB spectrum [dch][B] overlays the exchange buffer
-    float *pts = reinterpret_cast<float *>(smem + (size_t)G::GROUPS * G::BUF) + (size_t)grp * 4 * p.n_points;
+    float *pts = reinterpret_cast<float *>(smem + (size_t)G::GROUPS * G::BUF) + (size_t)grp * 4 * p.scratch_q;
     __shared__ float red_scratch[2 * (G::CTA > 32 ? G::CTA : 32)];
 
     const int s_raw = blockIdx.x * G::GROUPS + grp;

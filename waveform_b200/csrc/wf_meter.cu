@@ -7,12 +7,13 @@
 //                       (max over channels |x|)^2 -> sqrt(mean)
 //
 // HBM-bound integer/float streaming work, so the design is about touching each sample once:
-//   K1 block partials   every 256-sample block of the stream's timeline (history ring ++ new PCM) is reduced once
-//                       (sum of squares / max |x| / sum of (max_c |x_c|)^2), coalesced 128-byte warp loads;
-//   K2 window combine   one warp per (stream, tick, channel): whole blocks from the partials (L2-resident) + the two
-//                       ragged edges from the samples — O(W/256) instead of O(W) per tick, windows overlap W/hop times;
+//   K1 block partials   every block of the stream's timeline (history ring ++ new PCM) is reduced once (sum of squares /
+//                       max |x| / sum of (max_c |x_c|)^2) with 128-bit loads; the block size is the largest power of two
+//                       (32..256) dividing hop and W, so that windows are whole numbers of blocks whenever possible;
+//   K2 window combine   one warp per (stream, tick, channel): whole blocks from the partials (L2-resident) + ragged
+//                       edges from the samples if any — O(W/block) instead of O(W) per tick, windows overlap W/hop times;
 //   K3 recurrence       one thread per stream walks the ticks: sqrt/mean, EMA (fast-peaks rule), dBFS, m_last_silent;
-//   K4 history          the last W samples become the ring for the next call (double-buffered).
+//   (history)           K1 also writes the last W samples of the timeline into the (double-buffered) ring for the next call.
 // There is no CPU fallback.
 #include <cuda_runtime.h>
 
@@ -29,7 +30,7 @@
 
 namespace {
 
-constexpr int kBL = 256; // samples per partial block
+constexpr int kChunk = 256; // samples one warp reduces in K1 (8 per lane); partial blocks are 32..256 samples
 
 struct MParams {
     const float *pcm;
@@ -43,6 +44,8 @@ struct MParams {
     float *out_db, *out_lin;
     unsigned char *out_silent;
     int n_streams, n_ticks, hop, W, cc, pc, nblk, mode;
+    int bl;    // samples per partial: the largest power of two <= 256 dividing both hop and W (then windows have no ragged edges), else 256
+    int nchunk;// 256-sample chunks of the timeline (one warp each in K1)
     float g, g2;
     int tsmooth, fast_peaks;
     float floor_m10, db_min;
@@ -99,47 +102,107 @@ __device__ __forceinline__ float reduce_range(const Row &r0, const Row &r1, bool
     return acc;
 }
 
-// K1: one warp per (stream, partial channel, 256-sample block).  Blocks that lie wholly inside 16-byte aligned new PCM
-// (all but the few that touch the history ring or the end) take two 128-bit loads per lane.
+// K1: one warp per (stream, partial channel, 256-sample chunk): lane l reduces samples [8l, 8l+8) of the chunk, groups of
+// bl/8 lanes combine into one partial per bl-sample block.  Chunks that lie wholly inside 16-byte aligned new PCM (all
+// but the few that touch the history ring or the end) take two 128-bit loads per lane.  The same pass writes the last W
+// samples of the timeline into the ring for the next call (every sample is read exactly once here).
 template<int MODE>
 __global__ void meter_block_kernel(const MParams p, const int vec4)
 {
     const int warps_per_cta = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
-    const long long total = (long long)p.n_streams * p.pc * p.nblk;
+    const long long total = (long long)p.n_streams * p.pc * p.nchunk;
     const long long L = (long long)p.W + (long long)p.n_ticks * p.hop;
+    const long long tail0 = L - p.W; // timeline position of ring slot 0 of the next call
     const bool two = (MODE == WF_METER_INPUT_RMS) && p.cc > 1;
+    const int per = kChunk / p.bl;   // partials per chunk
+    const int glanes = p.bl / 8;     // lanes per partial
     for(long long w = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); w < total;
         w += (long long)gridDim.x * warps_per_cta)
     {
-        const int j = (int)(w % p.nblk);
-        const int c = (int)((w / p.nblk) % p.pc);
-        const int s = (int)(w / ((long long)p.nblk * p.pc));
-        const long long u0 = (long long)j * kBL;
+        const int j = (int)(w % p.nchunk);
+        const int c = (int)((w / p.nchunk) % p.pc);
+        const int s = (int)(w / ((long long)p.nchunk * p.pc));
+        const long long u0 = (long long)j * kChunk;
         const Row r0 = row_of(p, s, c);
         const Row r1 = two ? row_of(p, s, 1) : r0;
+        float *h0 = p.hist_next + ((size_t)s * p.cc + c) * p.W;
+        float *h1 = p.hist_next + ((size_t)s * p.cc + 1) * p.W;
         float acc = 0.0f;
-        if(vec4 && u0 >= p.W && u0 + kBL <= L)
+        const long long ul = u0 + 8 * lane; // my 8 samples
+        if(vec4 && u0 >= p.W && u0 + kChunk <= L)
         {
-            const float4 *q0 = reinterpret_cast<const float4 *>(r0.pcm + (u0 - p.W)) + lane;
-            const float4 a = __ldg(q0), b = __ldg(q0 + 32);
+            const float4 *q0 = reinterpret_cast<const float4 *>(r0.pcm + (ul - p.W));
+            const float4 a = __ldg(q0), b = __ldg(q0 + 1);
             float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
             if(two)
             {
-                const float4 *q1 = reinterpret_cast<const float4 *>(r1.pcm + (u0 - p.W)) + lane;
+                const float4 *q1 = reinterpret_cast<const float4 *>(r1.pcm + (ul - p.W));
                 a1 = __ldg(q1);
-                b1 = __ldg(q1 + 32);
+                b1 = __ldg(q1 + 1);
             }
             acc = combine<MODE>(combine<MODE>(contrib<MODE>(a.x, a1.x), contrib<MODE>(a.y, a1.y)),
                                 combine<MODE>(contrib<MODE>(a.z, a1.z), contrib<MODE>(a.w, a1.w)));
             acc = combine<MODE>(acc, combine<MODE>(combine<MODE>(contrib<MODE>(b.x, b1.x), contrib<MODE>(b.y, b1.y)),
                                                    combine<MODE>(contrib<MODE>(b.z, b1.z), contrib<MODE>(b.w, b1.w))));
+            if(ul + 8 > tail0)
+            {
+                // ring for the next call (tail0 is a multiple of 4 here: W, n_ticks*hop offsets keep 16-byte alignment
+                // only if hop is a multiple of 4 -> otherwise fall back to scalar stores)
+                if(ul >= tail0 && ((tail0 & 3) == 0))
+                {
+                    *reinterpret_cast<float4 *>(h0 + (ul - tail0)) = a;
+                    *reinterpret_cast<float4 *>(h0 + (ul - tail0) + 4) = b;
+                    if(two)
+                    {
+                        *reinterpret_cast<float4 *>(h1 + (ul - tail0)) = a1;
+                        *reinterpret_cast<float4 *>(h1 + (ul - tail0) + 4) = b1;
+                    }
+                }
+                else
+                {
+                    const float va[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    const float vb[8] = {a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for(int i = 0; i < 8; ++i)
+                        if(ul + i >= tail0)
+                        {
+                            h0[ul + i - tail0] = va[i];
+                            if(two)
+                                h1[ul + i - tail0] = vb[i];
+                        }
+                }
+            }
         }
         else
-            acc = reduce_range<MODE>(r0, r1, two, p.W, u0, min(u0 + kBL, L), lane, acc);
-        acc = warp_combine<MODE>(acc);
-        if(lane == 0)
-            p.partial[w] = acc;
+        {
+#pragma unroll
+            for(int i = 0; i < 8; ++i)
+            {
+                const long long u = ul + i;
+                if(u < L)
+                {
+                    const float x0 = vsample(r0, p.W, u);
+                    const float x1 = two ? vsample(r1, p.W, u) : 0.0f;
+                    acc = combine<MODE>(acc, contrib<MODE>(x0, x1));
+                    if(u >= tail0)
+                    {
+                        h0[u - tail0] = x0;
+                        if(two)
+                            h1[u - tail0] = x1;
+                    }
+                }
+            }
+        }
+        // combine inside each group of glanes lanes (= one partial of bl samples)
+        for(int o = 1; o < glanes; o <<= 1)
+            acc = combine<MODE>(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if((lane & (glanes - 1)) == 0)
+        {
+            const long long blk = (long long)j * per + lane / glanes;
+            if(blk < p.nblk)
+                p.partial[((size_t)s * p.pc + c) * p.nblk + blk] = acc;
+        }
     }
 }
 
@@ -158,17 +221,17 @@ __global__ void meter_window_kernel(const MParams p)
         const int t = (int)((w / p.pc) % p.n_ticks);
         const int s = (int)(w / ((long long)p.pc * p.n_ticks));
         const long long lo = (long long)(t + 1) * p.hop, hi = lo + p.W;
-        const long long jb = (lo + kBL - 1) / kBL, je = hi / kBL;
+        const long long jb = (lo + p.bl - 1) / p.bl, je = hi / p.bl;
         const Row r0 = row_of(p, s, c);
         const Row r1 = two ? row_of(p, s, 1) : r0;
         float acc = 0.0f;
         if(jb <= je)
         {
-            acc = reduce_range<MODE>(r0, r1, two, p.W, lo, jb * kBL, lane, acc);
+            acc = reduce_range<MODE>(r0, r1, two, p.W, lo, jb * p.bl, lane, acc);
             const float *part = p.partial + ((size_t)s * p.pc + c) * p.nblk;
             for(long long j = jb + lane; j < je; j += 32)
                 acc = combine<MODE>(acc, part[j]);
-            acc = reduce_range<MODE>(r0, r1, two, p.W, je * kBL, hi, lane, acc);
+            acc = reduce_range<MODE>(r0, r1, two, p.W, je * p.bl, hi, lane, acc);
         }
         else
             acc = reduce_range<MODE>(r0, r1, two, p.W, lo, hi, lane, acc);
@@ -224,24 +287,6 @@ __global__ void meter_scan_kernel(const MParams p)
     p.buf[2 * s] = buf[0];
     p.buf[2 * s + 1] = buf[1];
     p.flags[s] = last_silent ? 1 : 0;
-}
-
-// K4: ring for the next call = the last W samples of the timeline; grid.y = (stream, channel) rows
-__global__ void meter_hist_kernel(const MParams p)
-{
-    const long long shift = (long long)p.n_ticks * p.hop;
-    for(int row = blockIdx.y; row < p.n_streams * p.cc; row += gridDim.y)
-    {
-        const int s = row / p.cc, c = row % p.cc;
-        const float *hist = p.hist + (size_t)row * p.W;
-        const float *pcm = p.pcm + (size_t)s * p.stream_stride + (size_t)c * p.channel_stride;
-        float *dst = p.hist_next + (size_t)row * p.W;
-        for(int u = blockIdx.x * blockDim.x + threadIdx.x; u < p.W; u += gridDim.x * blockDim.x)
-        {
-            const long long v = u + shift;
-            dst[u] = (v < p.W) ? hist[v] : __ldg(pcm + (v - p.W));
-        }
-    }
 }
 
 __global__ void meter_fill_kernel(float *q, long long n, float v)
@@ -500,7 +545,16 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     const int cc = m->cfg.capture_channels, pc = m->pc, W = m->W;
     const size_t S = (size_t)b->n_streams, T = (size_t)b->n_ticks;
     const long long L = (long long)W + (long long)T * b->hop;
-    const int nblk = (int)((L + kBL - 1) / kBL);
+    int bl = kChunk;
+    {
+        int g = 32;
+        while(g * 2 <= kChunk && (b->hop % (g * 2)) == 0 && (W % (g * 2)) == 0)
+            g *= 2;
+        if((b->hop % g) == 0 && (W % g) == 0)
+            bl = g; // every window is a whole number of partial blocks
+    }
+    const int nchunk = (int)((L + kChunk - 1) / kChunk);
+    const int nblk = (int)((L + bl - 1) / bl);
     const bool dev_ptrs = m_is_device_ptr(b->pcm);
     const bool is_feed = m->cfg.mode == WF_METER_INPUT_RMS;
     const size_t out_n = S * T * (is_feed ? 1 : cc);
@@ -562,6 +616,8 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     p.cc = cc;
     p.pc = pc;
     p.nblk = nblk;
+    p.bl = bl;
+    p.nchunk = nchunk;
     p.mode = m->cfg.mode;
     {
         wf_config gc{};
@@ -579,7 +635,7 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     constexpr int kWarps = 8;
     // 128-bit loads need 16-byte aligned rows (W is a multiple of 16 samples already)
     const int vec4 = (((uintptr_t)d_pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->channel_stride & 3) == 0);
-    const int g1 = grid_for((long long)S * pc * nblk, kWarps, m->sm_count), g2 = grid_for((long long)S * T * pc, kWarps, m->sm_count);
+    const int g1 = grid_for((long long)S * pc * nchunk, kWarps, m->sm_count), g2 = grid_for((long long)S * T * pc, kWarps, m->sm_count);
     switch(m->cfg.mode)
     {
     case WF_METER_PEAK:
@@ -598,12 +654,7 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     WFM_CUDA(m, cudaGetLastError());
     meter_scan_kernel<<<(int)((S + 127) / 128), 128, 0, st>>>(p);
     WFM_CUDA(m, cudaGetLastError());
-    {
-        const dim3 hg((unsigned)std::min((W + 255) / 256, 64), (unsigned)std::min<size_t>(S * cc, 65535));
-        meter_hist_kernel<<<hg, 256, 0, st>>>(p);
-        WFM_CUDA(m, cudaGetLastError());
-    }
-    m->launches += 4;
+    m->launches += 3;
     WFM_CUDA(m, cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     // The ring is double-buffered per ENGINE, so a call must cover every stream whose history should survive: copy the

@@ -23,6 +23,7 @@
 #pragma once
 #include "wf_kernels.cuh"
 #include "wf_wide.cuh"
+#include "wf_fast2048.cuh"
 
 namespace wf {
 namespace v3 {
@@ -50,7 +51,10 @@ struct Geo3 {
     static constexpr int L1_ELEMS = A * S1;
     static constexpr int L2_ELEMS = B * SB;
     static constexpr int BUF = (L1_ELEMS > L2_ELEMS ? L1_ELEMS : L2_ELEMS); // one buffer serves L1, L2, X and the inbox
-    static constexpr int TPSM = (P <= 8) ? 1024 : 512; // resident threads per SM the register cap allows (64 / 128 registers)
+#ifndef WF_V3_TPSM
+#define WF_V3_TPSM 512
+#endif
+    static constexpr int TPSM = (P <= 8) ? 1024 : WF_V3_TPSM; // resident threads per SM the register cap allows (64 / 128 registers)
     static constexpr int MINB = (TPSM / TN) > 0 ? (TPSM / TN) : 1;
 };
 
@@ -389,8 +393,8 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             gather_sa = mapa(dbfull_sa, (unsigned)f);
         float peak = -INFINITY;
         bool outs0 = true, outs1 = true;
-        auto emit = [&](int d, int k, float outv, bool &outs) {
-            outs &= !(outv > p.floor_m10);
+        auto emit = [&](int d, int k, float outv, float &omax) {
+            omax = fmaxf(omax, outv); // "all outputs <= floor-10" == !(max > floor-10)
             if(EXTRA && k >= 1)
                 peak = fmaxf(peak, outv);
             if(odb != nullptr)
@@ -406,7 +410,10 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             }
         };
         auto finish = [&](float in, int k) -> float {
-            float outv = dbfs_mufu(in, p.db_min);
+            // dbfs (src/source.hpp:293-299) as MUFU.LG2 + FMUL + FMNMX: lg2.approx.ftz(0) = -inf and lg2(x < 0) = NaN both
+            // end up at DB_MIN = 20 log10(FLT_MIN) through the max (fmaxf drops a NaN); magnitudes below FLT_MIN (the
+            // far tail of an EMA decay, < -758.6 dBFS) report DB_MIN instead of a value below it, as wf_fast2048.cuh.
+            float outv = fmaxf(fast::lg2_approx_ftz(in) * 6.02059991327962390f, p.db_min);
             if(EXTRA && k >= 1)
             {
                 if(p.normalize)
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             // hot path: every channel processed this tick — straight-line code
             for(int d = 0; d < dch; ++d)
             {
-                bool outs = true;
+                float omax = -INFINITY;
 #pragma unroll
                 for(int i = 0; i < NST; ++i)
                 {
@@ -432,12 +439,12 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                     else
                         in = (CC == 2 && d == 1) ? st[CC - 1][i] : st[0][i];
                     const int k = bin_of(i);
-                    emit(d, k, finish(in, k), outs);
+                    emit(d, k, finish(in, k), omax);
                 }
                 if(d == 0)
-                    outs0 = outs;
+                    outs0 = !(omax > p.floor_m10);
                 else
-                    outs1 = outs;
+                    outs1 = !(omax > p.floor_m10);
             }
         }
         else
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             // rare paths: tick returned early (hold, :138-139) or a channel was skipped (stale dB re-converted)
             for(int d = 0; d < dch; ++d)
             {
-                bool outs = true;
+                float omax = -INFINITY;
 #pragma unroll 1
                 for(int i = 0; i < NST; ++i)
                 {
@@ -476,12 +483,12 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                         }
                         outv = finish(in, k);
                     }
-                    emit(d, k, outv, outs);
+                    emit(d, k, outv, omax);
                 }
                 if(d == 0)
-                    outs0 = outs;
+                    outs0 = !(omax > p.floor_m10);
                 else
-                    outs1 = outs;
+                    outs1 = !(omax > p.floor_m10);
             }
         }
         if(!last_silent && p.gate)

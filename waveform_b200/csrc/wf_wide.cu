@@ -12,7 +12,7 @@ namespace {
 template<int N, int CC, int R>
 cudaError_t launch_one(const KParams &kp, cudaStream_t st, bool display, int device)
 {
-    const size_t smem = wide::smem_bytes<N>(kp.dch, kp.n_points, display);
+    const size_t smem = wide::smem_bytes<N>(kp.dch, kp.scratch_q, display);
     static thread_local size_t configured[8] = {0};
     const int dev = device & 7;
     if(smem > 48 * 1024 && configured[dev] < smem)
