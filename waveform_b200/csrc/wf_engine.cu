@@ -48,7 +48,8 @@ struct wf_engine {
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
     float *d_tw = nullptr, *d_tw_post = nullptr;
-    float *d_tw1 = nullptr, *d_tw2 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
+    float *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw0 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
+    int fast_min_streams = 0;                  // WF_FAST_MIN_STREAMS: below this many streams N=2048 takes the cluster kernel (wf_v3.cuh)
     bool use_v3 = true;                        // WF_V3=0: fall back to the first-generation kernels (A/B tests)
     float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
     int *d_band_widths = nullptr, *d_band_offsets = nullptr;
@@ -244,7 +245,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.scratch_q, display) <= 227 * 1024)
         {
             const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
-            WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, st, display, e->device));
+            WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, display, e->device));
             e->launches++;
             return WF_OK;
         }
@@ -575,6 +576,9 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *wr = getenv("WF_WIDE_R");
         if(wr)
             e->wide_r = atoi(wr);
+        const char *fms = getenv("WF_FAST_MIN_STREAMS");
+        if(fms)
+            e->fast_min_streams = atoi(fms);
         const char *v3 = getenv("WF_V3");
         e->use_v3 = !(v3 && v3[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
@@ -617,10 +621,11 @@ int wf_create(const wf_config *cfg, wf_engine **out)
     WF_TRY(upload(e, &e->d_tw_post, t.tw_post));
     if(v3_supported(t.N))
     {
-        std::vector<float> tw1, tw2;
-        v3_build_twiddles(t.N, tw1, tw2);
+        std::vector<float> tw1, tw2, tw0;
+        v3_build_twiddles(t.N, tw1, tw2, tw0);
         WF_TRY(upload(e, &e->d_tw1, tw1));
         WF_TRY(upload(e, &e->d_tw2, tw2));
+        WF_TRY(upload(e, &e->d_tw0, tw0));
     }
     WF_TRY(upload(e, &e->d_interp_idx, t.interp_indices));
     WF_TRY(upload(e, &e->d_interp_w, t.interp_weights));
@@ -649,7 +654,7 @@ void wf_destroy(wf_engine *e)
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
     }
-    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_interp_idx, e->d_interp_w,
+    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_tw0, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
                     e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min};
     for(void *p : ptrs)
@@ -850,7 +855,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     }
     const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
     const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&
-                         !kp.out_min && aligned16 && !e->force_generic;
+                         !kp.out_min && aligned16 && !e->force_generic && kp.n_streams >= e->fast_min_streams;
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;

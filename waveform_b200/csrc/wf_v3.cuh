@@ -33,6 +33,9 @@ template<> struct Plan3<1024> { static constexpr int A = 8, B = 8, C = 8; };
 template<> struct Plan3<2048> { static constexpr int A = 16, B = 8, C = 8; };
 template<> struct Plan3<4096> { static constexpr int A = 16, B = 16, C = 8; };
 template<> struct Plan3<8192> { static constexpr int A = 16, B = 16, C = 16; };
+// 16384: a radix-2 first stage in registers, then TWO 4096-point sub-FFTs with the 8192 plan (32 points per thread as one
+// radix-32 pass spilled at 128 registers: the window and 31 twiddles are live next to the 32 points).  A = 32 only describes
+// the load pattern (32 points per thread, stride TN = 256).
 template<> struct Plan3<16384> { static constexpr int A = 32, B = 16, C = 16; };
 
 template<int N>
@@ -50,7 +53,10 @@ struct Geo3 {
     static constexpr int SB = A * SA;                     // L2 stride per kb
     static constexpr int L1_ELEMS = A * S1;
     static constexpr int L2_ELEMS = B * SB;
-    static constexpr int BUF = (L1_ELEMS > L2_ELEMS ? L1_ELEMS : L2_ELEMS); // one buffer serves L1, L2, X and the inbox
+    static constexpr bool SPLIT2 = (N == 16384);
+    static constexpr int WORK = (L1_ELEMS > L2_ELEMS ? L1_ELEMS : L2_ELEMS);
+    // one buffer serves L1, L2, X and the inbox; the split plan keeps X[M] apart from the sub-FFTs' work buffer
+    static constexpr int BUF = SPLIT2 ? (M + (B * (A / 2) * (C + 1) > (A / 2) * B * C ? B * (A / 2) * (C + 1) : (A / 2) * B * C)) : WORK;
 #ifndef WF_V3_TPSM
 #define WF_V3_TPSM 512
 #endif
@@ -61,6 +67,7 @@ struct Geo3 {
 struct Tw3 {
     const float2 *tw1; // [A][TN]  W_M^(t*ka)
     const float2 *tw2; // [B][C]   W_(B*C)^(c*kb)
+    const float2 *tw0; // split plan only: [16][TN] W_M^(a*TN + t) of the radix-2 first stage (tw1/tw2 are the half size's)
 };
 
 // dynamic shared memory of one CTA
@@ -102,28 +109,56 @@ struct Fft3 {
         for(int l = tid; l < N / 32; l += TN)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(frame + l * 32));
     }
-    // non-zero test (src/source_generic.cpp:63-76) + window multiply (:97-103); returns "any sample non-zero" (this thread)
-    static __device__ __forceinline__ bool finish_load(pk::c64 (&x)[P], const float2 (&v)[P], const float2 *window2, int tid)
+    // non-zero test (src/source_generic.cpp:63-76) + window multiply (:97-103); returns "any sample non-zero" (this thread).
+    // Split plan: the radix-2 first stage is fused in, pair by pair, so that window and twiddle values die immediately:
+    // x[a] = lo + hi (even bins' sub-FFT input), x[a + P/2] = (lo - hi) W_M^(a*TN + tid) (odd bins').
+    static __device__ __forceinline__ bool finish_load(pk::c64 (&x)[P], const float2 (&v)[P], const float2 *window2, int tid,
+                                                       const Tw3 &tw)
     {
         unsigned long long nzbits = 0;
-#pragma unroll
-        for(int a = 0; a < A; ++a)
+        if constexpr(!G::SPLIT2)
         {
-            x[a] = pk::from(v[a]);
-            nzbits |= x[a];
-        }
-        if(window2 != nullptr)
-        {
-            const pk::c64 *w = reinterpret_cast<const pk::c64 *>(window2) + tid;
 #pragma unroll
             for(int a = 0; a < A; ++a)
-                x[a] = pk::mul(x[a], __ldg(w + a * TN));
+            {
+                x[a] = pk::from(v[a]);
+                nzbits |= x[a];
+            }
+            if(window2 != nullptr)
+            {
+                const pk::c64 *w = reinterpret_cast<const pk::c64 *>(window2) + tid;
+#pragma unroll
+                for(int a = 0; a < A; ++a)
+                    x[a] = pk::mul(x[a], __ldg(w + a * TN));
+            }
+        }
+        else
+        {
+            const pk::c64 *w = reinterpret_cast<const pk::c64 *>(window2) + tid;
+            const pk::c64 *t0 = reinterpret_cast<const pk::c64 *>(tw.tw0) + tid;
+#pragma unroll
+            for(int a = 0; a < P / 2; ++a)
+            {
+                pk::c64 lo = pk::from(v[a]), hi = pk::from(v[a + P / 2]);
+                nzbits |= lo | hi;
+                if(window2 != nullptr)
+                {
+                    lo = pk::mul(lo, __ldg(w + a * TN));
+                    hi = pk::mul(hi, __ldg(w + (a + P / 2) * TN));
+                }
+                x[a] = pk::add(lo, hi);
+                x[a + P / 2] = pk::cmul(pk::sub(lo, hi), __ldg(t0 + a * TN));
+            }
         }
         return (nzbits & 0x7fffffff7fffffffull) != 0ull;
     }
 
-    // nz_thread: this thread saw a non-zero sample; returns the block-wide OR (folded into the first barrier)
-    static __device__ __forceinline__ bool run(pk::c64 (&x)[P], float2 *buf, const Tw3 &tw, int tid, bool nz_thread)
+    // The three passes.  Work buffer `buf` (L1 then L2); the natural-order result goes to out[k * OS] — `out` may be
+    // the work buffer itself (OS = 1, ALIAS) or another array (the split plan interleaves two sub-FFTs with OS = 2).
+    // nz_thread: this thread saw a non-zero sample; returns the block-wide OR (folded into the first barrier).
+    template<int OS, bool ALIAS>
+    static __device__ __forceinline__ bool run_core(pk::c64 (&x)[P], float2 *buf, const Tw3 &tw, int tid, bool nz_thread,
+                                                    pk::c64 *out)
     {
         pk::c64 *b64 = reinterpret_cast<pk::c64 *>(buf);
         bool nz;
@@ -181,7 +216,8 @@ struct Fft3 {
 #pragma unroll
                 for(int c = 0; c < C; ++c)
                     x[q * C + c] = src[q * (TN / A) * G::SB + c];
-            __syncthreads(); // L2 fully read before X (same memory) is written
+            if(ALIAS)
+                __syncthreads(); // L2 fully read before X (same memory) is written
 #pragma unroll
             for(int q = 0; q < G::LC; ++q)
             {
@@ -192,11 +228,37 @@ struct Fft3 {
                 pk::dft_bitrev<C>(y);
 #pragma unroll
                 for(int kc = 0; kc < C; ++kc)
-                    b64[tid + q * TN + kc * (A * B)] = y[bitrev<C>(kc)]; // X[ka + A*kb + AB*kc]
+                    out[(tid + q * TN + kc * (A * B)) * OS] = y[bitrev<C>(kc)]; // X[ka + A*kb + AB*kc]
             }
         }
-        __syncthreads();
+        if(ALIAS)
+            __syncthreads();
         return nz;
+    }
+    // v[a] windowed in x on entry; on exit X[k] sits in buf[k] (natural order)
+    static __device__ __forceinline__ bool run(pk::c64 (&x)[P], float2 *buf, const Tw3 &tw, int tid, bool nz_thread)
+    {
+        if constexpr(!G::SPLIT2)
+            return run_core<1, true>(x, buf, tw, tid, nz_thread, reinterpret_cast<pk::c64 *>(buf));
+        else
+        {
+            // radix-2 decimation in frequency: y0 = lo + hi -> even bins, y1 = (lo - hi) W_M^n -> odd bins; each half is a
+            // 4096-point FFT with exactly the 8192 plan's input layout (v[a] = y[a*256 + tid])
+            using H = Fft3<N / 2>;
+            pk::c64 *X = reinterpret_cast<pk::c64 *>(buf);
+            float2 *work = buf + M;
+            pk::c64 y0[P / 2], y1[P / 2];
+#pragma unroll
+            for(int a = 0; a < P / 2; ++a)
+            {
+                y0[a] = x[a];         // the radix-2 stage happened in finish_load
+                y1[a] = x[a + P / 2];
+            }
+            const bool nz = H::template run_core<2, false>(y0, work, tw, tid, nz_thread, X);
+            H::template run_core<2, false>(y1, work, tw, tid, false, X + 1);
+            __syncthreads(); // X complete
+            return nz;
+        }
     }
 };
 
@@ -510,9 +572,17 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     // PCM prefetch: with 16 points per thread the NEXT frame's samples are requested as soon as the current ones have
     // been windowed (in flight during the whole FFT); with 32 there is no register room until the split pass is over.
     constexpr bool EARLY_PF = (P <= 16) && (CC == 1); // two capture channels: no register room either -> L2 prefetch
+    // 32 points per thread: holding the next frame in 64 registers across a round makes ptxas spill them on arrival, so
+    // the frame is only pulled into L2 ahead of time and loaded where it is consumed.
+    constexpr bool KEEP_V = (P <= 16);
     float2 v[P];
     if((int)r < T)
-        F::load_raw(v, pcm_s + (size_t)r * p.hop, p.aligned8, tid);
+    {
+        if(KEEP_V)
+            F::load_raw(v, pcm_s + (size_t)r * p.hop, p.aligned8, tid);
+        else
+            F::prefetch_l2(pcm_s + (size_t)r * p.hop, tid);
+    }
 
     for(int t0 = 0; t0 < T; t0 += R)
     {
@@ -537,7 +607,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             for(int c = 0; c < CC; ++c)
             {
                 pk::c64 x[P];
-                const bool nzt = F::finish_load(x, v, p.window2, tid);
+                const bool nzt = F::finish_load(x, v, p.window2, tid, tw);
                 const float *nx = next_frame(c);
                 if(nx != nullptr)
                 {
@@ -580,7 +650,9 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                 for(int c = 0; c < CC; ++c)
                 {
                     pk::c64 x[P];
-                    const bool nzt = F::finish_load(x, v, p.window2, tid);
+                    if(!KEEP_V)
+                        F::load_raw(v, pcm_s + (size_t)c * p.channel_stride + (size_t)my_t * p.hop, p.aligned8, tid);
+                    const bool nzt = F::finish_load(x, v, p.window2, tid, tw);
                     const float *nx = next_frame(c);
                     if(nx != nullptr)
                     {
@@ -590,7 +662,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                             F::prefetch_l2(nx, tid);
                     }
                     const bool nz = F::run(x, buf, tw, tid, nzt);
-                    if(!EARLY_PF && c + 1 < CC)
+                    if(KEEP_V && !EARLY_PF && c + 1 < CC)
                         F::load_raw(v, nx, p.aligned8, tid); // the other channel of my tick
                     nzbits |= nz ? (1u << c) : 0u;
                     const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);
@@ -625,7 +697,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                     st_cluster_u32(mapa(smem_u32(&nzf[r]), (unsigned)tid), nzbits);
             }
             cluster_arrive(); // barrier B
-            if(!EARLY_PF && mine && my_t + R < T)
+            if(KEEP_V && !EARLY_PF && mine && my_t + R < T)
                 F::load_raw(v, pcm_s + (size_t)(my_t + R) * p.hop, p.aligned8, tid);
             cluster_wait();
 

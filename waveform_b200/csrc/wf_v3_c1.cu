@@ -25,10 +25,25 @@ size_t v3_smem_bytes(int N, int dch, int n_points, bool display)
     }
 }
 
-template<int N>
-static void build_tw(std::vector<float> &tw1, std::vector<float> &tw2)
+template<int NN>
+static void build_tw(std::vector<float> &tw1, std::vector<float> &tw2, std::vector<float> &tw0)
 {
+    // the split plan (16384) runs its sub-FFTs with the half size's tables and adds the radix-2 stage's W_M^(a*TN + t)
+    constexpr int N = v3::Geo3<NN>::SPLIT2 ? NN / 2 : NN;
     using G = v3::Geo3<N>;
+    tw0.clear();
+    if(v3::Geo3<NN>::SPLIT2)
+    {
+        using GG = v3::Geo3<NN>;
+        tw0.resize((size_t)(GG::P / 2) * GG::TN * 2);
+        for(int a = 0; a < GG::P / 2; ++a)
+            for(int t = 0; t < GG::TN; ++t)
+            {
+                const double ang = -2.0 * std::numbers::pi * (double)(a * GG::TN + t) / (double)GG::M;
+                tw0[2 * ((size_t)a * GG::TN + t)] = (float)std::cos(ang);
+                tw0[2 * ((size_t)a * GG::TN + t) + 1] = (float)std::sin(ang);
+            }
+    }
     tw1.resize((size_t)G::A * G::TN * 2);
     tw2.resize((size_t)G::B * G::C * 2);
     for(int ka = 0; ka < G::A; ++ka)
@@ -47,23 +62,24 @@ static void build_tw(std::vector<float> &tw1, std::vector<float> &tw2)
         }
 }
 
-void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2)
+void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2, std::vector<float> &tw0)
 {
     switch(N)
     {
-    case 1024: build_tw<1024>(tw1, tw2); break;
-    case 2048: build_tw<2048>(tw1, tw2); break;
-    case 4096: build_tw<4096>(tw1, tw2); break;
-    case 8192: build_tw<8192>(tw1, tw2); break;
-    case 16384: build_tw<16384>(tw1, tw2); break;
-    default: tw1.clear(); tw2.clear(); break;
+    case 1024: build_tw<1024>(tw1, tw2, tw0); break;
+    case 2048: build_tw<2048>(tw1, tw2, tw0); break;
+    case 4096: build_tw<4096>(tw1, tw2, tw0); break;
+    case 8192: build_tw<8192>(tw1, tw2, tw0); break;
+    case 16384: build_tw<16384>(tw1, tw2, tw0); break;
+    default: tw1.clear(); tw2.clear(); tw0.clear(); break;
     }
 }
 
 cudaError_t v3_launch(int N, int cc, int R, bool extra, const KParams &kp, const float *d_tw1, const float *d_tw2,
-                      cudaStream_t st, bool display, int device)
+                      const float *d_tw0, cudaStream_t st, bool display, int device)
 {
-    v3::Tw3 tw{reinterpret_cast<const float2 *>(d_tw1), reinterpret_cast<const float2 *>(d_tw2)};
+    v3::Tw3 tw{reinterpret_cast<const float2 *>(d_tw1), reinterpret_cast<const float2 *>(d_tw2),
+               reinterpret_cast<const float2 *>(d_tw0)};
     if(cc == 2)
         return v3_launch_c2(N, R, extra, kp, tw, st, display, device);
     return v3impl::launch_cc<1>(N, R, extra, kp, tw, st, display, device);
