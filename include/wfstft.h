@@ -270,6 +270,57 @@ int wf_meter_reset(wf_meter *m, int32_t first_stream, int32_t count);
 int64_t wf_meter_launch_count(const wf_meter *m);
 float wf_meter_last_kernel_ms(wf_meter *m);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Waveform (oscilloscope) mode — the third tick_* virtual behind the backend seam:
+ *   WAVSource::tick_waveform          src/source.hpp:277, src/source_generic.cpp:272-390
+ *   its setup                         src/source.cpp:1129-1143 (m_fft_size := m_width, m_waveform_samples, m_waveform_ts := 0),
+ *                                     :1243-1248 (start-up zeros in the capture ring), :1181 (m_decibels := DB_MIN)
+ * A wf_wave keeps, per stream, the scrolling buffer m_decibels[2][width] and m_last_silent, and per ENGINE the clock the
+ * reference derives from packet timestamps (m_audio_ts, m_waveform_ts).  One call = n_streams sources x n_ticks ticks; tick t
+ * is preceded by a capture packet of samples [t*hop, (t+1)*hop) of each channel whose end is stamped "now" (get_audio_sync
+ * == 0).  Every stream of the engine ticks in every call (the timing state is shared).  The nearest-sample resampling is
+ * integer arithmetic on nanosecond timestamps (bit-exact); the dBFS conversion uses log10f (last-bit differences). */
+typedef struct wf_wave_config {
+    uint32_t struct_size;     /* = sizeof(wf_wave_config) */
+    int32_t device;           /* CUDA device ordinal, -1 = current */
+    int32_t max_streams;
+    uint32_t sample_rate;
+    int32_t capture_channels; /* 1 or 2 */
+    int32_t stereo;           /* m_stereo */
+    int32_t width;            /* m_width: points of the scrolling buffer */
+    int32_t meter_ms;         /* m_meter_ms: time span shown */
+    int32_t normalize_volume; /* m_normalize_volume */
+    float volume_target;      /* m_volume_target */
+    float max_gain;           /* m_max_gain */
+} wf_wave_config;
+
+typedef struct wf_wave_batch {
+    uint32_t struct_size;     /* = sizeof(wf_wave_batch) */
+    int32_t n_streams;        /* must equal max_streams */
+    int32_t n_ticks;
+    int32_t hop;              /* samples per capture packet / tick (>= 1) */
+    const float *pcm;         /* planar float PCM, host or device; >= n_ticks*hop samples per channel */
+    int64_t stream_stride;
+    int64_t channel_stride;
+    const float *input_rms;   /* optional [n_streams][n_ticks] m_input_rms per tick (volume normalisation) */
+    float *out;               /* [n_streams][n_ticks][display_channels][width] m_decibels after the tick (oldest point first) */
+    uint8_t *out_silent;      /* optional [n_streams][n_ticks] m_last_silent after the tick */
+} wf_wave_batch;
+
+typedef struct wf_wave wf_wave;
+
+void wf_wave_config_init(wf_wave_config *cfg); /* plugin defaults: width 800, 150 ms (src/source.cpp:119-174) */
+int wf_wave_create(const wf_wave_config *cfg, wf_wave **out); /* ≙ WAVSource::update in waveform mode */
+void wf_wave_destroy(wf_wave *w);
+const char *wf_wave_last_error(const wf_wave *w);
+int wf_wave_process(wf_wave *w, const wf_wave_batch *batch);
+int wf_wave_process_async(wf_wave *w, const wf_wave_batch *batch, void *cuda_stream);
+/* ≙ the hidden / capture-timeout branch (src/source_generic.cpp:280-289): unless already silent, buffers := DB_MIN,
+ * m_last_silent := true, for every stream. */
+int wf_wave_reset(wf_wave *w);
+int64_t wf_wave_launch_count(const wf_wave *w);
+float wf_wave_last_kernel_ms(wf_wave *w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,12 @@ class WfoConfig(C.Structure):
     ]
 
 
+class WfoWaveConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("capture_channels", C.c_int32), ("stereo", C.c_int32), ("width", C.c_int32),
+                ("meter_ms", C.c_int32), ("normalize_volume", C.c_int32), ("volume_target", C.c_float),
+                ("max_gain", C.c_float)]
+
+
 class WfoMeterConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_uint32), ("capture_channels", C.c_int32), ("meter_ms", C.c_int32),
                 ("rms_mode", C.c_int32), ("tsmoothing", C.c_int32), ("gravity", C.c_float),
@@ -89,6 +95,10 @@ def lib():
                                   f32p, f32p]
     L.wfo_render_pixels.argtypes = [vp, f32p, f32p, f32p]
     L.wfo_r2c.argtypes = [f32p, C.c_int, f32p]
+    L.wfo_wave_create.restype = vp
+    L.wfo_wave_create.argtypes = [C.POINTER(WfoWaveConfig)]
+    L.wfo_wave_destroy.argtypes = [vp]
+    L.wfo_wave_run.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, f32p, f32p, C.POINTER(C.c_ubyte)]
     L.wfo_meter_window.argtypes = [C.POINTER(WfoMeterConfig)]
     L.wfo_meter_create.restype = vp
     L.wfo_meter_create.argtypes = [C.POINTER(WfoMeterConfig)]
@@ -355,3 +365,47 @@ class OracleMeter:
         self.L.wfo_meter_run(self.h, _fp(pcm[0]), _fp(pcm[1]) if cc > 1 else None, n_ticks, hop, seconds, _fp(db), _fp(lin),
                              None if sil is None else sil.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(r))
         return {"db": db, "lin": lin, "silent": sil, "rms": r}
+
+
+def wave_config_from_settings(settings: dict | None = None, sample_rate=48000, channels=2) -> WfoWaveConfig:
+    """Reference setting keys -> the waveform mode's POD config (defaults src/source.cpp:119-174)."""
+    s = dict(settings or {})
+    c = WfoWaveConfig()
+    c.sample_rate = sample_rate
+    mode = s.get("channel_mode", "mono")
+    c.stereo = int(mode == "stereo")
+    c.capture_channels = min(channels, 2) if mode != "single" else 1
+    c.width = int(s.get("width", 800))
+    c.meter_ms = int(s.get("meter_buf", 150))
+    c.normalize_volume = int(bool(s.get("normalize_volume", False)))
+    c.volume_target = float(s.get("volume_target", -8.0))
+    c.max_gain = float(s.get("max_gain", 30.0))
+    return c
+
+
+class OracleWave:
+    """tick_waveform restated (wf_oracle_meter.c)."""
+
+    def __init__(self, settings: dict | None = None, sample_rate=48000, channels=2):
+        self.L = lib()
+        self.cfg = wave_config_from_settings(settings, sample_rate, channels)
+        self.h = self.L.wfo_wave_create(C.byref(self.cfg))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.wfo_wave_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def run(self, pcm: np.ndarray, n_ticks: int, hop: int, rms: np.ndarray | None = None):
+        pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)
+        cc, dch = self.cfg.capture_channels, (2 if self.cfg.stereo else 1)
+        out = np.zeros((n_ticks, dch, self.cfg.width), np.float32)
+        sil = np.zeros(n_ticks, np.uint8)
+        if rms is not None:
+            rms = np.ascontiguousarray(rms, dtype=np.float32)
+        self.L.wfo_wave_run(self.h, _fp(pcm[0]), _fp(pcm[1]) if cc > 1 else None, n_ticks, hop, _fp(rms), _fp(out),
+                            sil.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return {"out": out, "silent": sil}

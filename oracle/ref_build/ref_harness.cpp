@@ -468,4 +468,29 @@ int wfref_run_meter(void *h, const float *pcm0, const float *pcm1, int n_ticks, 
     return n_ticks;
 }
 
+// Waveform (oscilloscope) mode through the reference's own capture/tick loop (display_mode = "waveform"): tick t is preceded
+// by a push of samples [t*hop, (t+1)*hop) stamped "now".  out [n_ticks][display_channels][m_width] = m_decibels after the
+// tick (src/source_generic.cpp:272-390); rms: optional forced m_input_rms per tick (volume normalisation).
+int wfref_run_wave(void *h, const float *pcm0, const float *pcm1, int n_ticks, int hop, float seconds, const float *rms,
+                   float *out, unsigned char *out_silent)
+{
+    auto r = static_cast<Ref *>(h);
+    auto p = r->probe.get();
+    const size_t outsz = p->fft_size();
+    const int dch = p->stereo() ? 2 : 1;
+    for(int t = 0; t < n_ticks; ++t)
+    {
+        r->clock_ns += audio_frames_to_ns(r->sample_rate, (uint64_t)hop);
+        wfref_push_audio(h, pcm0 + (size_t)t * hop, pcm1 ? pcm1 + (size_t)t * hop : nullptr, (uint32_t)hop, 0);
+        if(rms)
+            p->force_input_rms(true, rms[t]);
+        wfref_tick(h, seconds);
+        for(int c = 0; c < dch; ++c)
+            memcpy(out + ((size_t)t * dch + c) * outsz, p->decibels(c), outsz * sizeof(float));
+        if(out_silent)
+            out_silent[t] = p->last_silent() ? 1 : 0;
+    }
+    return n_ticks;
+}
+
 } // extern "C"

@@ -76,6 +76,7 @@ def lib():
     L.wfref_get_render_buf.argtypes = [vp, C.c_int, f32p]
     L.wfref_run_stft.argtypes = [vp, f32p, f32p, C.c_int64, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p,
                                  C.c_int, C.POINTER(C.c_ubyte)]
+    L.wfref_run_wave.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte)]
     L.wfref_run_meter.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte), f32p]
     _lib = L
     return L
@@ -294,3 +295,16 @@ class RefSource:
         self.L.wfref_run_meter(self.h, _fp(ch0), _fp(ch1), n_ticks, hop, seconds, _fp(db), _fp(lin),
                                silent.ctypes.data_as(C.POINTER(C.c_ubyte)), _fp(rms))
         return {"db": db, "lin": lin, "silent": silent, "rms": rms}
+
+    def run_wave(self, pcm: np.ndarray, n_ticks: int, hop: int, seconds: float = 1.0 / 60.0, rms: np.ndarray | None = None):
+        """Waveform (oscilloscope) mode (display_mode "waveform"): out=[T, display_channels, width] m_decibels after each tick."""
+        pcm = np.ascontiguousarray(np.atleast_2d(pcm), dtype=np.float32)
+        assert pcm.shape[1] >= n_ticks * hop
+        ch1 = pcm[1] if pcm.shape[0] > 1 else None
+        out = np.zeros((n_ticks, self.display_channels, self.fft_size), dtype=np.float32)
+        silent = np.zeros(n_ticks, dtype=np.uint8)
+        if rms is not None:
+            rms = np.ascontiguousarray(rms, dtype=np.float32)
+        self.L.wfref_run_wave(self.h, _fp(pcm[0]), _fp(ch1), n_ticks, hop, seconds, _fp(rms), _fp(out),
+                              silent.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return {"out": out, "silent": silent}

@@ -135,6 +135,25 @@ int wfo_meter_last_silent(const wfo_meter *m);
 void wfo_meter_run(wfo_meter *m, const float *pcm0, const float *pcm1, int n_ticks, int hop, float seconds,
                    float *out_db, float *out_lin, unsigned char *out_silent, float *out_rms);
 
+/* ---- waveform (oscilloscope) mode: src/source_generic.cpp:272-390, capture side src/source.cpp:1817-1888 ---- */
+typedef struct wfo_wave_config {
+    uint32_t sample_rate;
+    int32_t capture_channels; /* 1 or 2 */
+    int32_t stereo;           /* m_stereo */
+    int32_t width;            /* m_width: points in the scrolling buffer (m_fft_size in this mode) */
+    int32_t meter_ms;         /* m_meter_ms: time span of the buffer */
+    int32_t normalize_volume;
+    float volume_target, max_gain;
+} wfo_wave_config;
+typedef struct wfo_wave wfo_wave;
+wfo_wave *wfo_wave_create(const wfo_wave_config *cfg);
+void wfo_wave_destroy(wfo_wave *w);
+void wfo_wave_tick(wfo_wave *w, const float *const x[2], size_t n, float input_rms);
+int wfo_wave_last_silent(const wfo_wave *w);
+const float *wfo_wave_buffer(const wfo_wave *w, int ch);
+void wfo_wave_run(wfo_wave *w, const float *pcm0, const float *pcm1, int n_ticks, int hop, const float *input_rms,
+                  float *out, unsigned char *out_silent);
+
 #ifdef __cplusplus
 }
 #endif

@@ -226,3 +226,188 @@ void wfo_meter_run(wfo_meter *m, const float *pcm0, const float *pcm1, int n_tic
         }
     }
 }
+
+/* ============================================================================================================= */
+/* Waveform (oscilloscope) mode: WAVSourceGeneric::tick_waveform, src/source_generic.cpp:272-390, with the capture  */
+/* side of src/source.cpp:1817-1888 for packets whose end is stamped "now" (get_audio_sync() == 0, reserve == 0).   */
+/* Setup: src/source.cpp:1129-1143 (m_fft_size := m_width, m_waveform_samples, m_waveform_ts := 0), :1181 (DB_MIN).  */
+/* ============================================================================================================= */
+struct wfo_wave {
+    wfo_wave_config cfg;
+    size_t outsz;        /* m_fft_size = m_width */
+    size_t ws;           /* m_waveform_samples */
+    uint64_t clock, audio_ts, waveform_ts;
+    int output_channels; /* src/source.cpp:1171 */
+    float *dec[2];       /* m_decibels */
+    int last_silent;
+    size_t prefill;      /* zeros still pending in m_capturebufs: update() pushes m_fft_size of them, src/source.cpp:1243-1248 */
+};
+
+static uint64_t frames_to_ns(uint64_t sr, uint64_t frames) { return (uint64_t)(((__uint128_t)frames * 1000000000ull) / sr); }
+static uint64_t ns_to_frames(uint64_t sr, uint64_t ns) { return (uint64_t)(((__uint128_t)ns * sr) / 1000000000ull); }
+
+wfo_wave *wfo_wave_create(const wfo_wave_config *cfg)
+{
+    wfo_wave *w = (wfo_wave *)calloc(1, sizeof(*w));
+    w->cfg = *cfg;
+    w->outsz = (size_t)cfg->width;
+    w->ws = (size_t)((double)cfg->sample_rate * ((double)cfg->meter_ms / 1000.0));
+    w->clock = 10ull * 1000000000ull;
+    w->output_channels = ((cfg->capture_channels > 1) || cfg->stereo) ? 2 : 1;
+    w->prefill = w->outsz;
+    for(int c = 0; c < 2; ++c)
+    {
+        w->dec[c] = (float *)malloc(w->outsz * sizeof(float));
+        for(size_t i = 0; i < w->outsz; ++i)
+            w->dec[c][i] = wfo_db_min();
+    }
+    return w;
+}
+
+void wfo_wave_destroy(wfo_wave *w)
+{
+    if(!w)
+        return;
+    free(w->dec[0]);
+    free(w->dec[1]);
+    free(w);
+}
+
+int wfo_wave_last_silent(const wfo_wave *w) { return w->last_silent; }
+const float *wfo_wave_buffer(const wfo_wave *w, int ch) { return w->dec[ch]; }
+
+static void rotate_left(float *a, size_t k, size_t n)
+{
+    if(k == 0 || k >= n)
+        return;
+    float *tmp = (float *)malloc(k * sizeof(float));
+    memcpy(tmp, a, k * sizeof(float));
+    memmove(a, a + k, (n - k) * sizeof(float));
+    memcpy(a + (n - k), tmp, k * sizeof(float));
+    free(tmp);
+}
+
+/* one capture packet of n samples per channel ending "now", then one tick_waveform */
+void wfo_wave_tick(wfo_wave *w, const float *const x[2], size_t n, float input_rms)
+{
+    const uint32_t sr = w->cfg.sample_rate;
+    const int cc = w->cfg.capture_channels;
+    const size_t outsz = w->outsz;
+    w->clock += frames_to_ns(sr, n);
+    w->audio_ts = w->clock; /* timestamp + audio_len, src/source.cpp:1836 */
+    /* pending samples = the start-up zeros (first tick only) ++ the new packet; the ring keeps at most m_waveform_samples
+     * of them (src/source.cpp:1881-1884) and every tick consumes all (:327) */
+    const size_t avail = w->prefill + n;
+    const size_t total = (avail > w->ws) ? w->ws : avail;
+    const size_t skip = avail - total; /* oldest samples dropped */
+    float *pend[2] = {NULL, NULL};
+    for(int ch = 0; ch < cc; ++ch)
+    {
+        pend[ch] = (float *)calloc(avail ? avail : 1, sizeof(float));
+        memcpy(pend[ch] + w->prefill, x[ch], n * sizeof(float));
+    }
+    w->prefill = 0;
+    if(total == 0)
+    {
+        free(pend[0]);
+        free(pend[1]);
+        return; /* :296-298 */
+    }
+    size_t counts[2] = {0, 0};
+    unsigned silent_channels = 0;
+    const uint64_t step_ns = ((uint64_t)w->cfg.meter_ms * 1000000ull) / (uint64_t)outsz; /* :303 */
+    for(int ch = 0; ch < cc; ++ch)
+    {
+        const float *buf = pend[ch] + skip;
+        const uint64_t start_ts = w->audio_ts - frames_to_ns(sr, total);
+        const uint64_t stop_ts = w->audio_ts;
+        if((start_ts >= w->audio_ts) || (stop_ts > w->audio_ts))
+        {
+            free(pend[0]);
+            free(pend[1]);
+            return; /* :321-322 */
+        }
+        if(w->waveform_ts < start_ts)
+            w->waveform_ts = start_ts; /* :323-324 */
+        if((w->waveform_ts > stop_ts) && ((w->waveform_ts - stop_ts) > step_ns))
+            w->waveform_ts = start_ts; /* :325-326 */
+        for(size_t i = 0; i < outsz; ++i)
+        {
+            const uint64_t ts = w->waveform_ts + (i * step_ns);
+            if(ts >= stop_ts)
+                break;
+            if(ts < w->waveform_ts)
+                break;
+            uint64_t index = ns_to_frames(sr, w->audio_ts - ts);
+            if(index < 1u)
+                index = 1u;
+            if(index > total)
+                index = total; /* std::clamp(.., reserve_samples + 1, total_samples), :336 */
+            w->dec[ch][counts[ch]++] = buf[total - index];
+        }
+        rotate_left(w->dec[ch], counts[ch], outsz); /* :339 */
+        int silent = 1;
+        for(size_t i = 0; i < outsz; ++i)
+            if(w->dec[ch][i] != 0.0f)
+            {
+                silent = 0;
+                w->last_silent = 0;
+                break;
+            }
+        if(silent)
+            if(++silent_channels >= (unsigned)cc)
+                w->last_silent = 1;
+    }
+    free(pend[0]);
+    free(pend[1]);
+    w->waveform_ts += (counts[0] * step_ns); /* :358 */
+    const int dch = w->cfg.stereo ? 2 : 1;
+    if(w->last_silent)
+    {
+        for(int ch = 0; ch < dch; ++ch)
+            for(size_t i = 0; i < outsz; ++i)
+                w->dec[ch][i] = wfo_db_min();
+        return;
+    }
+    if(w->output_channels > cc)
+        memcpy(w->dec[1], w->dec[0], outsz * sizeof(float));
+    if(w->cfg.stereo)
+    {
+        for(int ch = 0; ch < 2; ++ch)
+            for(size_t i = outsz - counts[ch]; i < outsz; ++i)
+                w->dec[ch][i] = dbfs_m(fabsf(w->dec[ch][i]));
+    }
+    else if(cc > 1)
+    {
+        for(size_t i = outsz - counts[0]; i < outsz; ++i)
+            w->dec[0][i] = dbfs_m((fabsf(w->dec[0][i]) + fabsf(w->dec[1][i])) * 0.5f);
+    }
+    else
+    {
+        for(size_t i = outsz - counts[0]; i < outsz; ++i)
+            w->dec[0][i] = dbfs_m(fabsf(w->dec[0][i]));
+    }
+    if(w->cfg.normalize_volume)
+    {
+        const float vc = fminf(w->cfg.volume_target - dbfs_m(input_rms), w->cfg.max_gain);
+        for(int ch = 0; ch < dch; ++ch)
+            for(size_t i = outsz - counts[ch]; i < outsz; ++i)
+                w->dec[ch][i] += vc;
+    }
+}
+
+/* out [n_ticks][display_channels][width]; tick t consumes samples [t*hop, (t+1)*hop) */
+void wfo_wave_run(wfo_wave *w, const float *pcm0, const float *pcm1, int n_ticks, int hop, const float *input_rms,
+                  float *out, unsigned char *out_silent)
+{
+    const int dch = w->cfg.stereo ? 2 : 1;
+    for(int t = 0; t < n_ticks; ++t)
+    {
+        const float *x[2] = {pcm0 + (size_t)t * hop, pcm1 ? pcm1 + (size_t)t * hop : NULL};
+        wfo_wave_tick(w, x, (size_t)hop, input_rms ? input_rms[t] : 0.0f);
+        for(int c = 0; c < dch; ++c)
+            memcpy(out + ((size_t)t * dch + c) * w->outsz, w->dec[c], w->outsz * sizeof(float));
+        if(out_silent)
+            out_silent[t] = (unsigned char)w->last_silent;
+    }
+}

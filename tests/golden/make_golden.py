@@ -109,8 +109,36 @@ def main_meter():
         print("meter", name, "window", ref.fft_size, "silent ticks", int(r["silent"].sum()), "rms[-1]", float(r["rms"][-1]))
 
 
+# Waveform (oscilloscope) mode fixtures: m_decibels after every tick of the unmodified reference's tick_waveform
+# (src/source_generic.cpp:272-390).
+WAVE_CASES = {
+    "mono_mix_800_150ms": dict(settings={"width": 800, "meter_buf": 150}, channels=2, T=30, hop=800),
+    "stereo_300_50ms": dict(settings={"width": 300, "meter_buf": 50, "channel_mode": "stereo"}, channels=2, T=40, hop=441),
+    "silent_200_10ms": dict(settings={"width": 200, "meter_buf": 10}, channels=1, T=40, hop=1600),
+    "normalized_640_500ms": dict(settings={"width": 640, "meter_buf": 500, "channel_mode": "stereo",
+                                           "normalize_volume": True}, channels=2, T=30, hop=1024),
+}
+
+
+def main_wave():
+    for name, c in WAVE_CASES.items():
+        T, hop, ch = c["T"], c["hop"], c["channels"]
+        pcm = synth_pcm(1, ch, T * hop, seed=0xB200 + len(name))[0]
+        pcm[:, (T // 2) * hop: (2 * T // 3) * hop] = 0.0
+        rms = (0.05 + 0.2 * np.random.default_rng(5).uniform(size=T)).astype(np.float32) \
+            if c["settings"].get("normalize_volume") else None
+        ref = RefSource({"display_mode": "waveform", **c["settings"]}, impl=IMPL_GENERIC, channels=ch)
+        r = ref.run_wave(pcm, T, hop, rms=rms)
+        np.savez_compressed(OUT / f"wave_{name}.npz", settings=json.dumps(c["settings"]), channels=ch, hop=hop, n_ticks=T,
+                            pcm=pcm, rms=rms if rms is not None else np.zeros(0, np.float32), out=r["out"], silent=r["silent"])
+        print("wave", name, r["out"].shape, "silent ticks", int(r["silent"].sum()))
+
+
 if __name__ == "__main__":
     import sys
-    if "--meter-only" not in sys.argv:
+    if "--meter-only" not in sys.argv and "--wave-only" not in sys.argv:
         main()
-    main_meter()
+    if "--wave-only" not in sys.argv:
+        main_meter()
+    if "--meter-only" not in sys.argv:
+        main_wave()

@@ -1,0 +1,114 @@
+"""Waveform (oscilloscope) mode, tick_waveform: SURVEY.md §8(f) rank 4.
+
+CPU: the oracle restatement (oracle/wf_oracle_meter.c, wfo_wave_*) bit-exact against the compiled reference and against the
+committed golden fixtures.  GPU: the CUDA path (wf_wave_* through the C-ABI) against the oracle — which points are emitted and
+which sample each takes is integer arithmetic and must match exactly (checked through the DB_MIN pattern and the silent
+flags); the dBFS values agree to 1e-4 dB (log10f last-bit differences between glibc and CUDA).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import synth_pcm
+
+GOLD = sorted((Path(__file__).parent / "golden").glob("wave_*.npz"))
+
+WAVE_CASES = [
+    ({"width": 800, "meter_buf": 150}, 2, 800),                                   # defaults, two channels mixed to mono
+    ({"width": 800, "meter_buf": 150, "channel_mode": "stereo"}, 2, 800),
+    ({"width": 300, "meter_buf": 50}, 1, 441),
+    ({"width": 200, "meter_buf": 10}, 1, 1600),                                   # packet longer than the window: silent rule fires
+    ({"width": 640, "meter_buf": 500, "channel_mode": "stereo", "normalize_volume": True}, 2, 1024),
+    ({"width": 1000, "meter_buf": 20, "channel_mode": "stereo"}, 1, 333),         # mono capture shown as two channels
+]
+
+
+def _case(settings, ch, hop, T=50, S=1):
+    pcm = synth_pcm(S, ch, T * hop)
+    pcm[:, :, 20 * hop: 30 * hop] = 0.0
+    pcm[:, :, 33 * hop: 35 * hop] = 1.0  # |x| == 1 -> exactly 0.0 dBFS entries (the all-zero "silent" quirk's raw material)
+    rms = (0.05 + 0.2 * np.random.default_rng(3).uniform(size=(S, T))).astype(np.float32) \
+        if settings.get("normalize_volume") else None
+    return pcm, rms
+
+
+@pytest.mark.parametrize("settings,ch,hop", WAVE_CASES)
+def test_wave_oracle_is_bit_exact_vs_compiled_reference(settings, ch, hop):
+    refbind = pytest.importorskip("oracle.refbind")
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle.oraclebind import OracleWave
+
+    T = 50
+    pcm, rms = _case(settings, ch, hop, T)
+    r = refbind.RefSource({"display_mode": "waveform", **settings}, channels=ch)
+    ref = r.run_wave(pcm[0], T, hop, rms=None if rms is None else rms[0])
+    out = OracleWave(settings, channels=ch).run(pcm[0], T, hop, rms=None if rms is None else rms[0])
+    assert np.array_equal(ref["out"], out["out"])
+    assert np.array_equal(ref["silent"], out["silent"])
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_wave_oracle_against_reference_golden_vectors(path):
+    from oracle.oraclebind import OracleWave
+
+    z = np.load(path, allow_pickle=False)
+    settings = json.loads(str(z["settings"]))
+    rms = z["rms"] if z["rms"].size else None
+    out = OracleWave(settings, channels=int(z["channels"])).run(z["pcm"], int(z["n_ticks"]), int(z["hop"]), rms=rms)
+    assert np.array_equal(out["out"], z["out"]) and np.array_equal(out["silent"], z["silent"])
+
+
+def _oracle_batch(settings, ch, pcm, T, hop, rms):
+    from oracle.oraclebind import OracleWave
+
+    outs = [OracleWave(settings, channels=ch).run(pcm[s], T, hop, rms=None if rms is None else rms[s]) for s in range(pcm.shape[0])]
+    return np.stack([o["out"] for o in outs]), np.stack([o["silent"] for o in outs])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_ptrs", [False, True])
+@pytest.mark.parametrize("settings,ch,hop", WAVE_CASES)
+def test_gpu_wave_parity_vs_oracle(settings, ch, hop, device_ptrs):
+    from waveform_b200 import WaveEngine
+
+    S, T = 4, 50
+    pcm, rms = _case(settings, ch, hop, T, S)
+    ref, ref_sil = _oracle_batch(settings, ch, pcm, T, hop, rms)
+    eng = WaveEngine(settings, channels=ch, max_streams=S)
+    if device_ptrs:
+        import torch
+        o = eng.process(torch.from_numpy(pcm).cuda(), T, hop, input_rms=None if rms is None else torch.from_numpy(rms))
+        out, sil = o["out"].cpu().numpy(), o["silent"].cpu().numpy()
+    else:
+        o = eng.process(pcm, T, hop, input_rms=rms)
+        out, sil = o["out"], o["silent"]
+    assert np.array_equal(sil, ref_sil)
+    lo = ref < -700.0                     # DB_MIN entries: which points exist / took a zero sample — integer arithmetic
+    assert np.array_equal(out < -700.0, lo)
+    assert np.array_equal(out[lo], ref[lo])
+    assert np.max(np.abs(out[~lo] - ref[~lo])) < 1e-4
+    # state continues across calls (the clock, the scrolling buffer, m_last_silent)
+    eng2 = WaveEngine(settings, channels=ch, max_streams=S)
+    a = eng2.process(pcm[:, :, : 7 * hop], 7, hop, input_rms=None if rms is None else rms[:, :7])
+    b = eng2.process(pcm[:, :, 7 * hop:], T - 7, hop, input_rms=None if rms is None else rms[:, 7:])
+    assert np.array_equal(np.concatenate([a["out"], b["out"]], axis=1), o["out"] if not device_ptrs else out)
+    assert np.array_equal(np.concatenate([a["silent"], b["silent"]], axis=1), sil)
+
+
+@pytest.mark.gpu
+def test_gpu_wave_requires_all_streams_and_reset():
+    from waveform_b200 import WaveEngine, WfError
+
+    eng = WaveEngine({"width": 256, "meter_buf": 100}, channels=1, max_streams=3)
+    pcm = synth_pcm(3, 1, 4 * 800)
+    with pytest.raises(WfError):
+        eng.process(pcm[:2], 4, 800)        # a subset of the streams would desynchronise the shared clock
+    eng.process(pcm, 4, 800)
+    eng.reset()                              # hidden / capture-timeout branch: buffers := DB_MIN, m_last_silent := true
+    out = eng.process(np.zeros((3, 1, 800), np.float32), 1, 800)
+    assert out["out"].min() < -700.0

@@ -49,7 +49,7 @@ struct wf_engine {
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
     float *d_tw = nullptr, *d_tw_post = nullptr;
     float *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw0 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
-    int fast_min_streams = 0;                  // WF_FAST_MIN_STREAMS: below this many streams N=2048 takes the cluster kernel (wf_v3.cuh)
+    int fast_min_streams = 0;                   // WF_FAST_MIN_STREAMS: below this many streams N=2048 takes the cluster kernel (wf_v3.cuh)
     bool use_v3 = true;                        // WF_V3=0: fall back to the first-generation kernels (A/B tests)
     float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
     int *d_band_widths = nullptr, *d_band_offsets = nullptr;

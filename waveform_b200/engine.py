@@ -45,6 +45,8 @@ EXPORTS = [
     "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_preview_table",
     "wf_meter_config_init", "wf_meter_create", "wf_meter_destroy", "wf_meter_last_error", "wf_meter_window",
     "wf_meter_process", "wf_meter_process_async", "wf_meter_reset", "wf_meter_launch_count", "wf_meter_last_kernel_ms",
+    "wf_wave_config_init", "wf_wave_create", "wf_wave_destroy", "wf_wave_last_error", "wf_wave_process",
+    "wf_wave_process_async", "wf_wave_reset", "wf_wave_launch_count", "wf_wave_last_kernel_ms",
 ]
 
 METER_PEAK, METER_RMS, METER_INPUT_RMS = 0, 1, 2
@@ -55,6 +57,22 @@ class WfMeterConfig(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_streams", C.c_int32), ("sample_rate", C.c_uint32),
         ("capture_channels", C.c_int32), ("mode", C.c_int32), ("meter_ms", C.c_int32), ("tsmoothing", C.c_int32),
         ("gravity", C.c_float), ("fast_peaks", C.c_int32), ("floor_db", C.c_int32),
+    ]
+
+
+class WfWaveConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_streams", C.c_int32), ("sample_rate", C.c_uint32),
+        ("capture_channels", C.c_int32), ("stereo", C.c_int32), ("width", C.c_int32), ("meter_ms", C.c_int32),
+        ("normalize_volume", C.c_int32), ("volume_target", C.c_float), ("max_gain", C.c_float),
+    ]
+
+
+class WfWaveBatch(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("n_streams", C.c_int32), ("n_ticks", C.c_int32), ("hop", C.c_int32),
+        ("pcm", C.c_void_p), ("stream_stride", C.c_int64), ("channel_stride", C.c_int64),
+        ("input_rms", C.c_void_p), ("out", C.c_void_p), ("out_silent", C.c_void_p),
     ]
 
 
@@ -165,6 +183,18 @@ def load_library():
     L.wf_meter_launch_count.argtypes = [vp]
     L.wf_meter_last_kernel_ms.restype = C.c_float
     L.wf_meter_last_kernel_ms.argtypes = [vp]
+    L.wf_wave_config_init.argtypes = [C.POINTER(WfWaveConfig)]
+    L.wf_wave_create.argtypes = [C.POINTER(WfWaveConfig), C.POINTER(vp)]
+    L.wf_wave_destroy.argtypes = [vp]
+    L.wf_wave_last_error.restype = C.c_char_p
+    L.wf_wave_last_error.argtypes = [vp]
+    L.wf_wave_process.argtypes = [vp, C.POINTER(WfWaveBatch)]
+    L.wf_wave_process_async.argtypes = [vp, C.POINTER(WfWaveBatch), vp]
+    L.wf_wave_reset.argtypes = [vp]
+    L.wf_wave_launch_count.restype = C.c_int64
+    L.wf_wave_launch_count.argtypes = [vp]
+    L.wf_wave_last_kernel_ms.restype = C.c_float
+    L.wf_wave_last_kernel_ms.argtypes = [vp]
     _lib = L
     return L
 
@@ -520,4 +550,101 @@ class MeterEngine:
             self._check(self.L.wf_meter_process(self.h, C.byref(b)))
         else:
             self._check(self.L.wf_meter_process_async(self.h, C.byref(b), 1 if stream == 0 else stream))
+        return out
+
+
+def make_wave_config(settings: dict | None = None, sample_rate: int = 48000, channels: int = 2, max_streams: int = 1,
+                     device: int = -1) -> WfWaveConfig:
+    """Reference setting keys (width, meter_buf, channel_mode, normalize_volume, volume_target, max_gain) -> wf_wave_config."""
+    L = load_library()
+    c = WfWaveConfig()
+    L.wf_wave_config_init(C.byref(c))
+    s = dict(settings or {})
+    c.device, c.max_streams, c.sample_rate = device, max_streams, sample_rate
+    mode = s.pop("channel_mode", "mono")
+    c.stereo = int(mode == "stereo")
+    c.capture_channels = min(channels, 2) if mode != "single" else 1
+    c.width = int(s.pop("width", 800))
+    c.meter_ms = int(s.pop("meter_buf", 150))
+    c.normalize_volume = int(bool(s.pop("normalize_volume", False)))
+    c.volume_target = float(s.pop("volume_target", -8.0))
+    c.max_gain = float(s.pop("max_gain", 30.0))
+    if s:
+        raise KeyError(f"unsupported waveform settings: {sorted(s)}")
+    return c
+
+
+class WaveEngine:
+    """Waveform (oscilloscope) mode (tick_waveform) on the GPU: ctypes over wf_wave_*; no DSP here."""
+
+    def __init__(self, settings: dict | None = None, sample_rate: int = 48000, channels: int = 2, max_streams: int = 1,
+                 device: int = -1):
+        self.L = load_library()
+        self.cfg = make_wave_config(settings, sample_rate, channels, max_streams, device)
+        h = C.c_void_p()
+        rc = self.L.wf_wave_create(C.byref(self.cfg), C.byref(h))
+        if rc != WF_OK:
+            raise WfError(rc, f"{self.L.wf_strerror(rc).decode()}: {self.L.wf_wave_last_error(None).decode()}")
+        self.h = h
+        self.display_channels = 2 if self.cfg.stereo else 1
+
+    def _check(self, rc):
+        if rc != WF_OK:
+            raise WfError(rc, f"{self.L.wf_strerror(rc).decode()}: {self.L.wf_wave_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.wf_wave_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.wf_wave_launch_count(self.h))
+
+    def last_kernel_ms(self) -> float:
+        return float(self.L.wf_wave_last_kernel_ms(self.h))
+
+    def reset(self):
+        self._check(self.L.wf_wave_reset(self.h))
+
+    def process(self, pcm, n_ticks: int, hop: int, *, input_rms=None, stream=None):
+        """pcm: [max_streams, capture_channels, >= n_ticks*hop] float32, numpy (host) or CUDA torch tensor.
+        Returns dict(out=[S, T, display_channels, width], silent=[S, T])."""
+        is_torch = hasattr(pcm, "data_ptr")
+        if pcm.ndim == 2:
+            pcm = pcm[None]
+        S, cc, ns = pcm.shape
+        if cc != self.cfg.capture_channels:
+            raise ValueError(f"pcm has {cc} channels, engine captures {self.cfg.capture_channels}")
+        if ns < n_ticks * hop:
+            raise ValueError(f"need {n_ticks * hop} samples per channel, got {ns}")
+        if is_torch:
+            import torch
+            assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=pcm.device)
+            f32, u8 = torch.float32, torch.uint8
+            if input_rms is not None:
+                input_rms = input_rms.to(device=pcm.device, dtype=f32).contiguous()
+        else:
+            pcm = np.ascontiguousarray(pcm, dtype=np.float32)
+            mk = lambda shape, dt: np.empty(shape, dtype=dt)
+            f32, u8 = np.float32, np.uint8
+            if input_rms is not None:
+                input_rms = np.ascontiguousarray(input_rms, dtype=np.float32)
+        out = {"out": mk((S, n_ticks, self.display_channels, self.cfg.width), f32), "silent": mk((S, n_ticks), u8)}
+        b = WfWaveBatch()
+        b.struct_size = C.sizeof(WfWaveBatch)
+        b.n_streams, b.n_ticks, b.hop = S, n_ticks, hop
+        b.pcm, b.stream_stride, b.channel_stride = _ptr(pcm), cc * ns, ns
+        b.input_rms, b.out, b.out_silent = _ptr(input_rms), _ptr(out["out"]), _ptr(out["silent"])
+        if stream is None:
+            self._check(self.L.wf_wave_process(self.h, C.byref(b)))
+        else:
+            self._check(self.L.wf_wave_process_async(self.h, C.byref(b), 1 if stream == 0 else stream))
         return out
