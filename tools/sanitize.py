@@ -25,3 +25,19 @@ for s, ch, S, T, hopdiv, pts in CASES:
     o2 = Engine(s, channels=ch, max_streams=S).process(x, T, hop, want_points=pts, input_rms=rms)  # host-pointer path
     assert np.array_equal(o["db"].cpu().numpy(), o2["db"])
     print(s.get("fft_size"), "ok", float(o["db"].float().mean()), flush=True)
+
+# level meter, RMS feed and waveform mode (host-pointer path, history shorter and longer than the window)
+from waveform_b200 import MeterEngine, WaveEngine
+from waveform_b200.engine import METER_INPUT_RMS
+for mode, st in ((None, {"meter_buf": 20, "rms_mode": True}), (None, {"meter_buf": 50, "rms_mode": False}), (METER_INPUT_RMS, {})):
+    m = MeterEngine(st, channels=2, max_streams=3, mode=mode)
+    x = synth_pcm(3, 2, 9 * 441)
+    a = m.process(x[:, :, : 4 * 441], 4, 441); b = m.process(torch.from_numpy(x[:, :, 4 * 441:]).cuda(), 5, 441)
+    torch.cuda.synchronize()
+    print("meter", mode, "ok", flush=True)
+for st, ch in (({"width": 300, "meter_buf": 50, "channel_mode": "stereo"}, 2), ({"width": 200, "meter_buf": 10}, 1)):
+    w = WaveEngine(st, channels=ch, max_streams=3)
+    x = synth_pcm(3, ch, 9 * 800)
+    a = w.process(x[:, :, : 4 * 800], 4, 800); b = w.process(torch.from_numpy(x[:, :, 4 * 800:]).cuda(), 5, 800)
+    torch.cuda.synchronize()
+    print("wave", st["width"], "ok", flush=True)

@@ -70,11 +70,18 @@ struct Tw3 {
     const float2 *tw0; // split plan only: [16][TN] W_M^(a*TN + t) of the radix-2 first stage (tw1/tw2 are the half size's)
 };
 
-// dynamic shared memory of one CTA
+// Cluster sizes > 1 with N <= 8192 keep the magnitude inbox in its own double-buffered array: one cluster barrier per round
+// instead of two (at 16384 that memory would halve the CTAs per SM, so the inbox aliases the FFT buffer there).
 template<int N>
-constexpr size_t smem_bytes(int dch, int n_points, bool display)
+constexpr bool dbuf_inbox() { return N <= 8192; }
+
+// dynamic shared memory of one CTA (cc = capture channels, R = cluster size)
+template<int N>
+constexpr size_t smem_bytes(int dch, int n_points, bool display, int cc, int R)
 {
     size_t b = (size_t)Geo3<N>::BUF * sizeof(float2);
+    if(R > 1 && dbuf_inbox<N>())
+        b += (size_t)2 * cc * (N / 2) * sizeof(float);
     if(display)
         b += (size_t)dch * (N / 2) * sizeof(float) + (size_t)4 * n_points * sizeof(float);
     return b;
@@ -280,11 +287,13 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
-    float *inbox = reinterpret_cast<float *>(smem_raw);       // [R][CC][SLICE] linear magnitudes (after barrier A)
-    float *dbfull = reinterpret_cast<float *>(buf + G::BUF); // [dch][B] dB spectrum of MY tick (display mode)
+    constexpr bool DBUF = (R > 1) && v3::dbuf_inbox<N>();
+    // [parity][R][CC][SLICE] linear magnitudes: own array (DBUF) or the FFT buffer itself (after barrier A)
+    float *inbox0 = DBUF ? reinterpret_cast<float *>(buf + G::BUF) : reinterpret_cast<float *>(smem_raw);
+    float *dbfull = reinterpret_cast<float *>(buf + G::BUF) + (DBUF ? 2 * CC * B : 0); // [dch][B] dB spectrum of MY tick
     float *pts = dbfull + (size_t)p.dch * B;
     __shared__ float red_scratch[2 * TN];
-    __shared__ unsigned nzf[R];
+    __shared__ unsigned nzf[2][R];
     __shared__ unsigned redf[2][R];
 
     const int tid = threadIdx.x;
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     const bool stereo = p.stereo != 0;
     const bool want_points = (p.out_points != nullptr) || (p.out_pixels != nullptr) || (p.out_min != nullptr);
     const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
-    const uint32_t inbox_sa = smem_u32(inbox);
+    const uint32_t inbox_sa0 = smem_u32(inbox0);
     const uint32_t dbfull_sa = smem_u32(dbfull);
 
     // Bin bookkeeping.  Phase 1 produces, per thread, the pairs j < HP:  k1 = tid + j*TN  and  k2 = M - k1
@@ -672,9 +681,16 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                         split_pair(X, twp, j, magr[c][2 * j], magr[c][2 * j + 1]);
                 }
             }
-            __syncthreads(); // my FFT buffer is free: it becomes the inbox
-            cluster_arrive(); // barrier A
-            cluster_wait();
+            const int par = DBUF ? ((t0 / R) & 1) : 0;
+            const uint32_t inbox_sa = inbox_sa0 + (uint32_t)(par * CC * B * sizeof(float));
+            const float *inbox = inbox0 + par * CC * B;
+            if constexpr(!DBUF)
+            {
+                __syncthreads(); // my FFT buffer is free: it becomes the inbox
+                cluster_arrive(); // barrier A
+                cluster_wait();
+            }
+            // (DBUF: inbox[par] was last read two rounds ago, before every peer arrived at the previous round's barrier)
             // ---- phase 2: all-to-all through distributed shared memory ----
             if(mine)
             {
@@ -694,7 +710,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                         st_cluster_f32(d2, magr[c][2 * j + 1]);
                     }
                 if(tid < R)
-                    st_cluster_u32(mapa(smem_u32(&nzf[r]), (unsigned)tid), nzbits);
+                    st_cluster_u32(mapa(smem_u32(&nzf[par][r]), (unsigned)tid), nzbits);
             }
             cluster_arrive(); // barrier B
             if(KEEP_V && !EARLY_PF && mine && my_t + R < T)
@@ -705,7 +721,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             for(int f = 0; f < nf; ++f)
             {
                 const int t = t0 + f;
-                const unsigned nzb = nzf[f];
+                const unsigned nzb = nzf[par][f];
                 const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
                 bool proc[2] = {false, false};
                 unsigned silent_channels = 0;

@@ -9,7 +9,7 @@ namespace wf {
 struct KParams;
 bool v3_supported(int N);
 int v3_min_cluster(int N); // smallest supported cluster size (1, or 2 where the per-thread state would not fit registers)
-size_t v3_smem_bytes(int N, int dch, int n_points, bool display);
+size_t v3_smem_bytes(int N, int dch, int n_points, bool display, int cc, int R);
 // Inter-pass twiddle tables (interleaved re,im), evaluated in double: tw1[ka][t] = W_M^(t*ka), tw2[kb][c] = W_(BC)^(c*kb);
 // tw0 (16384 only) = W_M^(a*TN + t) of the radix-2 first stage, tw1/tw2 then belong to the 4096-point sub-FFTs
 void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2, std::vector<float> &tw0);

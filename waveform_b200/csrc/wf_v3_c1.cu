@@ -12,15 +12,15 @@ cudaError_t v3_launch_c2(int N, int R, bool extra, const KParams &kp, const v3::
 bool v3_supported(int N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384; }
 int v3_min_cluster(int N) { return (N <= 8192) ? 1 : 2; }
 
-size_t v3_smem_bytes(int N, int dch, int n_points, bool display)
+size_t v3_smem_bytes(int N, int dch, int n_points, bool display, int cc, int R)
 {
     switch(N)
     {
-    case 1024: return v3::smem_bytes<1024>(dch, n_points, display);
-    case 2048: return v3::smem_bytes<2048>(dch, n_points, display);
-    case 4096: return v3::smem_bytes<4096>(dch, n_points, display);
-    case 8192: return v3::smem_bytes<8192>(dch, n_points, display);
-    case 16384: return v3::smem_bytes<16384>(dch, n_points, display);
+    case 1024: return v3::smem_bytes<1024>(dch, n_points, display, cc, R);
+    case 2048: return v3::smem_bytes<2048>(dch, n_points, display, cc, R);
+    case 4096: return v3::smem_bytes<4096>(dch, n_points, display, cc, R);
+    case 8192: return v3::smem_bytes<8192>(dch, n_points, display, cc, R);
+    case 16384: return v3::smem_bytes<16384>(dch, n_points, display, cc, R);
     default: return 0;
     }
 }

@@ -11,7 +11,7 @@ namespace v3impl {
 template<int N, int CC, int R, bool EXTRA>
 cudaError_t launch_one(const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
 {
-    const size_t smem = v3::smem_bytes<N>(kp.dch, kp.scratch_q, display);
+    const size_t smem = v3::smem_bytes<N>(kp.dch, kp.scratch_q, display, CC, R);
     static thread_local size_t configured[8] = {0};
     const int dev = device & 7;
     if(smem > 48 * 1024 && configured[dev] < smem)
