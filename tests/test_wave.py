@@ -90,7 +90,10 @@ def test_gpu_wave_parity_vs_oracle(settings, ch, hop, device_ptrs):
     assert np.array_equal(sil, ref_sil)
     lo = ref < -700.0                     # DB_MIN entries: which points exist / took a zero sample — integer arithmetic
     assert np.array_equal(out < -700.0, lo)
-    assert np.array_equal(out[lo], ref[lo])
+    untouched = ref == np.float32(-758.59564)  # never-converted or zero-sample entries without volume compensation
+    assert np.array_equal(out[untouched], ref[untouched])
+    # DB_MIN + volume compensation: the compensation itself goes through log10f (1 ulp between glibc and CUDA)
+    assert np.max(np.abs(out[lo] - ref[lo]), initial=0.0) < 1e-3
     assert np.max(np.abs(out[~lo] - ref[~lo])) < 1e-4
     # state continues across calls (the clock, the scrolling buffer, m_last_silent)
     eng2 = WaveEngine(settings, channels=ch, max_streams=S)
