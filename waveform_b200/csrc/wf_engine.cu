@@ -244,7 +244,8 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         const bool display = kp.out_points || kp.out_pixels || kp.out_min;
         if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.scratch_q, display, CC, 8) <= 227 * 1024)
         {
-            const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+            const bool feat = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask;
+            const int x = feat ? 3 : (kp.out_peak ? 1 : 0);
             WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, display, e->device));
             e->launches++;
             return WF_OK;

@@ -271,8 +271,10 @@ struct Fft3 {
 
 } // namespace v3
 
-// EXTRA compiles in slope / fast peaks / skip mask / volume normalisation / roll-off / peak output.
-template<int N, int CC, int R, bool EXTRA>
+// EXTRA: 0 = plain, 1 = + per-tick peak output (BASELINE config 5), 3 = + slope / fast peaks / skip mask / volume
+// normalisation / roll-off as well.  Keeping the peak apart matters: ncu on config 5 (profiles/r01m_v3_c5.txt) showed the
+// all-features epilogue costing 54 warp-instructions per bin although only the peak was in use.
+template<int N, int CC, int R, int EXTRA>
 __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     stft_v3_kernel(const __grid_constant__ KParams p, const __grid_constant__ v3::Tw3 tw)
 {
@@ -285,6 +287,8 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     constexpr int SP = SLICE / TN; // bins owned by one thread
     static_assert(SP >= 1 && SP * TN * R == B, "cluster size does not tile the bins");
 
+    constexpr bool XP = (EXTRA & 1) != 0; // peak output
+    constexpr bool XF = (EXTRA & 2) != 0; // slope, fast peaks, skip mask, volume normalisation, roll-off
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     constexpr bool DBUF = (R > 1) && v3::dbuf_inbox<N>();
@@ -410,14 +414,13 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         return do_proc;
     };
     // EMA of one bin, src/source_generic.cpp:124-132
+    // (without temporal smoothing the engine passes g = 0, g2 = 1: 0*old + 1*mag == mag exactly, no branch needed)
+    const float ema_g = p.g, ema_g2 = p.g2;
     auto ema = [&](float mag, float &state, bool do_proc) {
-        if(p.tsmooth)
-        {
-            float oldval = state;
-            if(EXTRA && p.fast_peaks)
-                oldval = fmaxf(mag, oldval);
-            mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
-        }
+        float oldval = state;
+        if(XF && p.fast_peaks)
+            oldval = fmaxf(mag, oldval);
+        mag = __fadd_rn(__fmul_rn(ema_g, oldval), __fmul_rn(ema_g2, mag));
         if(do_proc)
             state = mag;
     };
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             p2 = (tid == 0) ? pm : p2;
         }
         pk::c64 m = pk::mul(pk::make(sqrt_mufu(p1), sqrt_mufu(p2)), pk::make(p.coef_half, p.coef_half));
-        if(EXTRA && p.slope != nullptr)
+        if(XF && p.slope != nullptr)
             m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + ((j == 0) ? k2_first : k2_base - j * TN))));
         pk::split(m, m1, m2);
     };
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     auto do_outputs = [&](int t, int f, const bool (&proc)[2]) {
         const float *prev_db = (p.out_db != nullptr && t > 0) ? p.out_db + ((size_t)s * T + (t - 1)) * dch * B : hold_s;
         float vc = 0.0f;
-        if(EXTRA && p.normalize)
+        if(XF && p.normalize)
         {
             const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + t] : 0.0f;
             vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         bool outs0 = true, outs1 = true;
         auto emit = [&](int d, int k, float outv, float &omax) {
             omax = fmaxf(omax, outv); // "all outputs <= floor-10" == !(max > floor-10)
-            if(EXTRA && k >= 1)
+            if(XP && k >= 1)
                 peak = fmaxf(peak, outv);
             if(odb != nullptr)
                 stg_stream(odb + d * B + k, outv);
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             // end up at DB_MIN = 20 log10(FLT_MIN) through the max (fmaxf drops a NaN); magnitudes below FLT_MIN (the
             // far tail of an EMA decay, < -758.6 dBFS) report DB_MIN instead of a value below it, as wf_fast2048.cuh.
             float outv = fmaxf(fast::lg2_approx_ftz(in) * 6.02059991327962390f, p.db_min);
-            if(EXTRA && k >= 1)
+            if(XF && k >= 1)
             {
                 if(p.normalize)
                     outv += vc; // :161-167
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         }
         if(p.out_silent != nullptr && r == 0 && tid == 0)
             p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
-        if(EXTRA && p.out_peak != nullptr)
+        if(XP && p.out_peak != nullptr)
         {
             const float gm = group_max<TN>(peak, red_scratch);
             if(tid == 0)
@@ -609,7 +612,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         {
             // ---- one CTA per stream: FFT -> gate -> split pass -> EMA per channel, all in registers ----
             const int t = t0;
-            const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
+            const bool skip_all = XF && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
             bool proc[2] = {false, false};
             unsigned silent_channels = 0;
 #pragma unroll
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             {
                 const int t = t0 + f;
                 const unsigned nzb = nzf[par][f];
-                const bool skip_all = EXTRA && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
+                const bool skip_all = XF && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
                 bool proc[2] = {false, false};
                 unsigned silent_channels = 0;
 #pragma unroll

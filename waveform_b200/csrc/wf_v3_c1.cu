@@ -6,7 +6,7 @@
 
 namespace wf {
 
-cudaError_t v3_launch_c2(int N, int R, bool extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display,
+cudaError_t v3_launch_c2(int N, int R, int extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display,
                          int device);
 
 bool v3_supported(int N) { return N == 1024 || N == 2048 || N == 4096 || N == 8192 || N == 16384; }
@@ -75,7 +75,7 @@ void v3_build_twiddles(int N, std::vector<float> &tw1, std::vector<float> &tw2, 
     }
 }
 
-cudaError_t v3_launch(int N, int cc, int R, bool extra, const KParams &kp, const float *d_tw1, const float *d_tw2,
+cudaError_t v3_launch(int N, int cc, int R, int extra, const KParams &kp, const float *d_tw1, const float *d_tw2,
                       const float *d_tw0, cudaStream_t st, bool display, int device)
 {
     v3::Tw3 tw{reinterpret_cast<const float2 *>(d_tw1), reinterpret_cast<const float2 *>(d_tw2),

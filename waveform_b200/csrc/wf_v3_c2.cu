@@ -3,7 +3,7 @@
 
 namespace wf {
 
-cudaError_t v3_launch_c2(int N, int R, bool extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display,
+cudaError_t v3_launch_c2(int N, int R, int extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display,
                          int device)
 {
     return v3impl::launch_cc<2>(N, R, extra, kp, tw, st, display, device);

@@ -8,7 +8,7 @@
 namespace wf {
 namespace v3impl {
 
-template<int N, int CC, int R, bool EXTRA>
+template<int N, int CC, int R, int EXTRA>
 cudaError_t launch_one(const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
 {
     const size_t smem = v3::smem_bytes<N>(kp.dch, kp.scratch_q, display, CC, R);
@@ -37,7 +37,7 @@ cudaError_t launch_one(const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bo
     return cudaLaunchKernelEx(&cfg, stft_v3_kernel<N, CC, R, EXTRA>, kp, tw);
 }
 
-template<int N, int CC, bool EXTRA>
+template<int N, int CC, int EXTRA>
 cudaError_t launch_r(int R, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
 {
     switch(R)
@@ -55,25 +55,30 @@ cudaError_t launch_r(int R, const KParams &kp, const v3::Tw3 &tw, cudaStream_t s
 }
 
 template<int CC>
-cudaError_t launch_cc(int N, int R, bool extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
+cudaError_t launch_cc(int N, int R, int extra, const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
 {
     switch(N)
     {
     case 1024:
-        return extra ? launch_r<1024, CC, true>(R, kp, tw, st, display, device)
-                     : launch_r<1024, CC, false>(R, kp, tw, st, display, device);
+        return (extra == 0)   ? launch_r<1024, CC, 0>(R, kp, tw, st, display, device)
+               : (extra == 1) ? launch_r<1024, CC, 1>(R, kp, tw, st, display, device)
+                              : launch_r<1024, CC, 3>(R, kp, tw, st, display, device);
     case 2048:
-        return extra ? launch_r<2048, CC, true>(R, kp, tw, st, display, device)
-                     : launch_r<2048, CC, false>(R, kp, tw, st, display, device);
+        return (extra == 0)   ? launch_r<2048, CC, 0>(R, kp, tw, st, display, device)
+               : (extra == 1) ? launch_r<2048, CC, 1>(R, kp, tw, st, display, device)
+                              : launch_r<2048, CC, 3>(R, kp, tw, st, display, device);
     case 4096:
-        return extra ? launch_r<4096, CC, true>(R, kp, tw, st, display, device)
-                     : launch_r<4096, CC, false>(R, kp, tw, st, display, device);
+        return (extra == 0)   ? launch_r<4096, CC, 0>(R, kp, tw, st, display, device)
+               : (extra == 1) ? launch_r<4096, CC, 1>(R, kp, tw, st, display, device)
+                              : launch_r<4096, CC, 3>(R, kp, tw, st, display, device);
     case 8192:
-        return extra ? launch_r<8192, CC, true>(R, kp, tw, st, display, device)
-                     : launch_r<8192, CC, false>(R, kp, tw, st, display, device);
+        return (extra == 0)   ? launch_r<8192, CC, 0>(R, kp, tw, st, display, device)
+               : (extra == 1) ? launch_r<8192, CC, 1>(R, kp, tw, st, display, device)
+                              : launch_r<8192, CC, 3>(R, kp, tw, st, display, device);
     case 16384:
-        return extra ? launch_r<16384, CC, true>(R, kp, tw, st, display, device)
-                     : launch_r<16384, CC, false>(R, kp, tw, st, display, device);
+        return (extra == 0)   ? launch_r<16384, CC, 0>(R, kp, tw, st, display, device)
+               : (extra == 1) ? launch_r<16384, CC, 1>(R, kp, tw, st, display, device)
+                              : launch_r<16384, CC, 3>(R, kp, tw, st, display, device);
     default: return cudaErrorInvalidValue;
     }
 }
