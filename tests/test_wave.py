@@ -23,7 +23,8 @@ WAVE_CASES = [
     ({"width": 300, "meter_buf": 50}, 1, 441),
     ({"width": 200, "meter_buf": 10}, 1, 1600),                                   # packet longer than the window: silent rule fires
     ({"width": 640, "meter_buf": 500, "channel_mode": "stereo", "normalize_volume": True}, 2, 1024),
-    ({"width": 1000, "meter_buf": 20, "channel_mode": "stereo"}, 1, 333),         # mono capture shown as two channels
+    ({"width": 1000, "meter_buf": 20, "channel_mode": "stereo"}, 1, 333),         # mono capture shown as two channels: the
+                                                                                  # copy's newest points stay RAW (quirk)
 ]
 
 
@@ -92,9 +93,10 @@ def test_gpu_wave_parity_vs_oracle(settings, ch, hop, device_ptrs):
     assert np.array_equal(out < -700.0, lo)
     untouched = ref == np.float32(-758.59564)  # never-converted or zero-sample entries without volume compensation
     assert np.array_equal(out[untouched], ref[untouched])
+    raw = (~lo) & (np.abs(ref) <= 1.0) & (ref == out)  # raw samples kept by the reference (gathers are exact)
     # DB_MIN + volume compensation: the compensation itself goes through log10f (1 ulp between glibc and CUDA)
     assert np.max(np.abs(out[lo] - ref[lo]), initial=0.0) < 1e-3
-    assert np.max(np.abs(out[~lo] - ref[~lo])) < 1e-4
+    assert np.max(np.abs(out[~lo & ~raw] - ref[~lo & ~raw]), initial=0.0) < 1e-4
     # state continues across calls (the clock, the scrolling buffer, m_last_silent)
     eng2 = WaveEngine(settings, channels=ch, max_streams=S)
     a = eng2.process(pcm[:, :, : 7 * hop], 7, hop, input_rms=None if rms is None else rms[:, :7])

@@ -232,7 +232,7 @@ int pick_v3_r(const wf_engine *e, const KParams &kp)
     if(e->wide_r == 1 || e->wide_r == 2 || e->wide_r == 4 || e->wide_r == 8)
         return std::max(rmin, e->wide_r);
     int r = rmin;
-    while(r < 8 && (long long)kp.n_streams * r < 3LL * e->sm_count && 2 * r <= kp.n_frames)
+    while(r < 8 && (long long)kp.n_streams * r * 3 < 5LL * e->sm_count && 2 * r <= kp.n_frames) // per-tick overhead grows with R
         r *= 2;
     return r;
 }

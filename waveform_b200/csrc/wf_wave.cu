@@ -119,14 +119,19 @@ __global__ void __launch_bounds__(256) wave_kernel(const WParams p)
                     pos += (pos < 0) ? W : 0;
                     if(p.stereo)
                     {
-                        float a = dbfs_dev(fabsf(r0[pos]), p.db_min), b = dbfs_dev(fabsf(r1[pos]), p.db_min);
+                        float a = dbfs_dev(fabsf(r0[pos]), p.db_min);
                         if(p.normalize)
-                        {
                             a += vc;
-                            b += vc;
-                        }
                         r0[pos] = a;
-                        r1[pos] = b;
+                        // counts[1] stays 0 for a single capture channel (:371-375): the second display channel keeps
+                        // the RAW new samples of the whole-buffer copy above — reproduced as is
+                        if(p.cc > 1)
+                        {
+                            float b = dbfs_dev(fabsf(r1[pos]), p.db_min);
+                            if(p.normalize)
+                                b += vc;
+                            r1[pos] = b;
+                        }
                     }
                     else
                     {
