@@ -108,3 +108,47 @@ def test_product_never_imports_the_oracle():
         assert "oraclebind" not in txt and "refbind" not in txt and "wf_oracle" not in txt and "liboracle" not in txt, f
     out = subprocess.run(["ldd", str(ROOT / "waveform_b200" / "lib" / "libwfstft.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "fftw" not in out.lower()
+
+
+def test_meter_and_wave_struct_layouts_match_header(tmp_path):
+    from waveform_b200.engine import WfMeterBatch, WfMeterConfig, WfWaveBatch, WfWaveConfig
+
+    src = tmp_path / "sz2.c"
+    src.write_text('#include "wfstft.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(wf_meter_config), sizeof(wf_meter_batch),'
+                   'sizeof(wf_wave_config), sizeof(wf_wave_batch), offsetof(wf_meter_batch,pcm), offsetof(wf_meter_batch,out_silent),'
+                   'offsetof(wf_wave_batch,pcm), offsetof(wf_wave_batch,out_silent));return 0;}\n')
+    exe = tmp_path / "sz2"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [C.sizeof(WfMeterConfig), C.sizeof(WfMeterBatch), C.sizeof(WfWaveConfig),
+                                    C.sizeof(WfWaveBatch), WfMeterBatch.pcm.offset, WfMeterBatch.out_silent.offset,
+                                    WfWaveBatch.pcm.offset, WfWaveBatch.out_silent.offset]
+
+
+def test_meter_and_wave_fail_loudly_without_a_gpu_and_reject_bad_configs():
+    """wf_meter_create / wf_wave_create: argument errors first (-1 / -7), then WF_ERR_NO_DEVICE (-4) — never a CPU path."""
+    import torch
+    from waveform_b200 import MeterEngine, WaveEngine, WfError
+    from waveform_b200.engine import WfMeterConfig, WfWaveConfig, load_library
+
+    L = load_library()
+    h = C.c_void_p()
+    mc = WfMeterConfig()
+    L.wf_meter_config_init(C.byref(mc))
+    mc.capture_channels = 3
+    assert L.wf_meter_create(C.byref(mc), C.byref(h)) == -1 and not h.value
+    mc.capture_channels = 2
+    mc.struct_size = 4
+    assert L.wf_meter_create(C.byref(mc), C.byref(h)) == -7
+    wc = WfWaveConfig()
+    L.wf_wave_config_init(C.byref(wc))
+    assert (wc.width, wc.meter_ms, wc.struct_size) == (800, 150, C.sizeof(WfWaveConfig))
+    wc.width = 0
+    assert L.wf_wave_create(C.byref(wc), C.byref(h)) == -1 and not h.value
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the no-device branch cannot be exercised")
+    for ctor in (lambda: MeterEngine({}, channels=2), lambda: WaveEngine({}, channels=2)):
+        with pytest.raises(WfError) as ei:
+            ctor()
+        assert ei.value.status == -4 and "no CPU fallback" in str(ei.value)
