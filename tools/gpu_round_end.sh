@@ -22,4 +22,5 @@ for l in "1024 64" "512 128" "256 256"; do set -- $l
   echo "layout streams=$1 frames=$2 (cluster kernel, WF_FAST_MIN_STREAMS=1000000)"; WF_FAST_MIN_STREAMS=1000000 lay $1 $2
 done | tee -a gpurun_out/layouts.txt
 timeout 200 python tools/bench_shapes.py 2>&1 | tee gpurun_out/shapes.txt
+WF_WIDE_R=4 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 300 compute-sanitizer --tool memcheck python tools/sanitize.py 2>&1 | tail -4 | tee gpurun_out/sanitizer.txt
 timeout 100 python tools/bench_meter.py 2>&1 | tee gpurun_out/meter.txt

@@ -49,7 +49,10 @@ struct wf_engine {
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
     float *d_tw = nullptr, *d_tw_post = nullptr;
     float *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw0 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
-    int fast_min_streams = 0;                   // WF_FAST_MIN_STREAMS: below this many streams N=2048 takes the cluster kernel (wf_v3.cuh)
+    // N=2048: the warp-per-stream kernel needs ~2400 streams to fill the GPU; with fewer streams AND long per-stream tick
+    // sequences (>= 32) the cluster kernel (wf_v3.cuh, up to 8 ticks of a stream in flight) is faster: measured 256x256
+    // 96 -> 145 M, 512x128 185 -> 202 M, 1024x64 286 vs 242 M spectra/s (profiles/r01_layouts.txt).  WF_FAST_MIN_STREAMS overrides.
+    int fast_min_streams = 768;
     bool use_v3 = true;                        // WF_V3=0: fall back to the first-generation kernels (A/B tests)
     float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
     int *d_band_widths = nullptr, *d_band_offsets = nullptr;
@@ -856,7 +859,8 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     }
     const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
     const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&
-                         !kp.out_min && aligned16 && !e->force_generic && kp.n_streams >= e->fast_min_streams;
+                         !kp.out_min && aligned16 && !e->force_generic &&
+                         (kp.n_streams >= e->fast_min_streams || kp.n_frames < 32 || !e->use_v3);
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
