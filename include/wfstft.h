@@ -318,6 +318,12 @@ int wf_wave_process_async(wf_wave *w, const wf_wave_batch *batch, void *cuda_str
 /* ≙ the hidden / capture-timeout branch (src/source_generic.cpp:280-289): unless already silent, buffers := DB_MIN,
  * m_last_silent := true, for every stream. */
 int wf_wave_reset(wf_wave *w);
+/* The host-side plan of a call made right after wf_wave_create (no device needed; lets a CPU-only test check the integer
+ * timestamp walk against the plugin): counts[t] = points emitted by tick t; src (optional, `capacity` entries) = for every
+ * point in order the index of the sample it takes in the call's PCM, or -1 for a start-up zero.  Returns the total number of
+ * points or a negative status. */
+int64_t wf_wave_preview_plan(const wf_wave_config *cfg, int32_t n_ticks, int32_t hop, int32_t *counts, int32_t *src,
+                             int64_t capacity);
 int64_t wf_wave_launch_count(const wf_wave *w);
 float wf_wave_last_kernel_ms(wf_wave *w);
 

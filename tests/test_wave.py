@@ -64,6 +64,28 @@ def test_wave_oracle_against_reference_golden_vectors(path):
     assert np.array_equal(out["out"], z["out"]) and np.array_equal(out["silent"], z["silent"])
 
 
+@pytest.mark.parametrize("width,meter_ms,hop", [(800, 150, 800), (300, 50, 441), (1000, 20, 333), (200, 10, 1600), (640, 500, 1024)])
+def test_engine_timestamp_walk_equals_the_reference(width, meter_ms, hop):
+    """No GPU needed: libwfstft's host-side plan (which points a tick emits, which sample each takes) against the oracle.
+    A mono capture shown as two channels leaves the RAW new samples in the second channel (reference quirk), so a ramp input
+    reveals the sample index the reference picked for every point."""
+    from oracle.oraclebind import OracleWave
+    from waveform_b200.engine import make_wave_config, preview_wave_plan
+
+    T = 40
+    settings = {"width": width, "meter_buf": meter_ms, "channel_mode": "stereo"}
+    ramp = ((np.arange(T * hop, dtype=np.float64) + 1.0) * 2.0 ** -20).astype(np.float32)[None, :]  # exact, never 0
+    ref = OracleWave(settings, channels=1).run(ramp, T, hop)["out"][:, 1, :]
+    counts, src = preview_wave_plan(make_wave_config(settings, channels=1), T, hop)
+    assert counts.min() >= 0 and counts.max() <= width and counts.sum() == len(src)
+    o = 0
+    for t in range(T):
+        c = int(counts[t])
+        want = np.where(src[o: o + c] >= 0, ramp[0, np.maximum(src[o: o + c], 0)], np.float32(0.0))
+        assert np.array_equal(ref[t, width - c:], want), t
+        o += c
+
+
 def _oracle_batch(settings, ch, pcm, T, hop, rms):
     from oracle.oraclebind import OracleWave
 

@@ -555,6 +555,34 @@ int wf_wave_reset(wf_wave *w)
     return WF_OK;
 }
 
+int64_t wf_wave_preview_plan(const wf_wave_config *cfg, int32_t n_ticks, int32_t hop, int32_t *counts, int32_t *src,
+                             int64_t capacity)
+{
+    if(!cfg || n_ticks < 0 || hop < 1)
+        return WF_ERR_INVALID_ARG;
+    if(cfg->struct_size != sizeof(wf_wave_config))
+        return WF_ERR_ABI;
+    if(cfg->sample_rate < 1 || cfg->width < 1 || cfg->width > 8192 || cfg->meter_ms < 1 ||
+       ((uint64_t)cfg->meter_ms * 1000000ull) / (uint64_t)cfg->width == 0)
+        return WF_ERR_INVALID_ARG;
+    wf_wave w; // host-only use: the same initial clock / start-up state wf_wave_create sets up
+    w.cfg = *cfg;
+    w.ws = (size_t)((double)cfg->sample_rate * ((double)cfg->meter_ms / 1000.0));
+    w.prefill = (size_t)cfg->width;
+    std::vector<int> s, off;
+    plan_ticks(&w, n_ticks, hop, s, off);
+    if(counts)
+        for(int t = 0; t < n_ticks; ++t)
+            counts[t] = off[t + 1] - off[t];
+    if(src)
+    {
+        if((int64_t)s.size() > capacity)
+            return WF_ERR_INVALID_ARG;
+        memcpy(src, s.data(), s.size() * sizeof(int));
+    }
+    return (int64_t)s.size();
+}
+
 int64_t wf_wave_launch_count(const wf_wave *w) { return w ? w->launches : 0; }
 
 float wf_wave_last_kernel_ms(wf_wave *w)

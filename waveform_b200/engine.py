@@ -46,7 +46,7 @@ EXPORTS = [
     "wf_meter_config_init", "wf_meter_create", "wf_meter_destroy", "wf_meter_last_error", "wf_meter_window",
     "wf_meter_process", "wf_meter_process_async", "wf_meter_reset", "wf_meter_launch_count", "wf_meter_last_kernel_ms",
     "wf_wave_config_init", "wf_wave_create", "wf_wave_destroy", "wf_wave_last_error", "wf_wave_process",
-    "wf_wave_process_async", "wf_wave_reset", "wf_wave_launch_count", "wf_wave_last_kernel_ms",
+    "wf_wave_process_async", "wf_wave_reset", "wf_wave_launch_count", "wf_wave_last_kernel_ms", "wf_wave_preview_plan",
 ]
 
 METER_PEAK, METER_RMS, METER_INPUT_RMS = 0, 1, 2
@@ -195,6 +195,8 @@ def load_library():
     L.wf_wave_launch_count.argtypes = [vp]
     L.wf_wave_last_kernel_ms.restype = C.c_float
     L.wf_wave_last_kernel_ms.argtypes = [vp]
+    L.wf_wave_preview_plan.restype = C.c_int64
+    L.wf_wave_preview_plan.argtypes = [C.POINTER(WfWaveConfig), C.c_int32, C.c_int32, vp, vp, C.c_int64]
     _lib = L
     return L
 
@@ -648,3 +650,15 @@ class WaveEngine:
         else:
             self._check(self.L.wf_wave_process_async(self.h, C.byref(b), 1 if stream == 0 else stream))
         return out
+
+
+def preview_wave_plan(cfg: WfWaveConfig, n_ticks: int, hop: int):
+    """(counts[n_ticks], src[total]) of the first call after wf_wave_create — host arithmetic only, no device."""
+    L = load_library()
+    counts = np.zeros(n_ticks, np.int32)
+    total = L.wf_wave_preview_plan(C.byref(cfg), n_ticks, hop, counts.ctypes.data, None, 0)
+    if total < 0:
+        raise WfError(int(total), L.wf_strerror(int(total)).decode())
+    src = np.zeros(max(int(total), 1), np.int32)
+    L.wf_wave_preview_plan(C.byref(cfg), n_ticks, hop, counts.ctypes.data, src.ctypes.data, int(total))
+    return counts, src[: int(total)]
