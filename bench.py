@@ -9,7 +9,13 @@ One "step" = one pass of the hot path over one batch of synthetic 48 kHz PCM alr
 so that the EMA recurrence state stays on-chip between frames.  Inputs (512 MiB)
 and outputs (256 MiB) are each larger than the 126 MB L2, so every step streams from/to HBM.
 
-The JSON line printed by rank 0 follows the driver's contract; see DESIGN.md §Measurement for the fields.
+Besides the contract's keys the line carries:
+  parity            the measured launch (same engine geometry, fresh state) against the reference's generic CPU path on a
+                    sample of streams: SURVEY.md §8(d) "first 256 frames/shard" + streams from the far ends of the grid
+  config.extra      the other layouts of the same 65 536-frame batch (65536x1 ... 256x256) with their roofline fractions,
+                    a strong-scaling number (65 536 frames TOTAL over the N GPUs) and BASELINE.json configs[4]
+                    (N=16384, 128 streams x 256 ticks per GPU, NCCL MAX all-reduce + normalise pass inside the timed loop)
+  cpu_baseline      all-cores AVX2 (the value) plus AVX2 on one core and the generic path on one core
 """
 from __future__ import annotations
 
@@ -33,11 +39,14 @@ SETTINGS = {"fft_size": 2048, "window": "hann", "temporal_smoothing": "exp_movin
 N_FFT = 2048
 BINS = N_FFT // 2
 BYTES_PER_FRAME = N_FFT * 4 + BINS * 4  # PCM in + bins out
+STATE_BYTES_PER_STREAM = 2 * BINS * 4   # EMA state read + written once per stream and launch (reported separately, §8(d))
+LAYOUTS = [(65536, 1), (16384, 4), (8192, 8), (4096, 16), (2048, 32), (1024, 64), (512, 128), (256, 256)]
+ALL_CPUS = sorted(os.sched_getaffinity(0))  # the CPUs this process may use, before any NUMA binding
 
 
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
-    (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None if there is no capture."""
+    (profiles/traffic.json, written by tools/ncu_summary.py --traffic from the raw CSV next to it); None if absent."""
     p = ROOT / "profiles" / "traffic.json"
     try:
         d = json.loads(p.read_text())
@@ -60,22 +69,24 @@ def load_peaks():
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own implementation (oracle/_ref), or the oracle port if _ref is absent
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_throughput(frames_per_thread: int, threads: int, chunk_frames: int = 512):
+def cpu_reference_throughput(frames_per_thread: int, threads: int, chunk_frames: int = 512, impl: str = "avx2"):
     """Spectra/s of the reference's CPU path on `threads` host threads, N=2048 Hann EMA dBFS.
 
-    Each thread owns one WAVSourceAVX2 (+ its FFTW plan) and walks `frames_per_thread` consecutive frames
+    Each thread owns one WAVSource (+ its FFTW plan) and walks `frames_per_thread` consecutive frames
     (hop = N) of its own channel through capture_audio()/tick(); the PCM chunk is reused so it stays in cache,
     which is how the plugin sees audio too.  ctypes releases the GIL, so the threads run in parallel.
+    impl: "avx2" = WAVSourceAVX2 (what the plugin runs on this class of CPU), "generic" = WAVSourceGeneric (the parity target).
     """
     import numpy as np
 
     from oracle import refbind
 
     kind = "reference"
-    use_ref = refbind.available()
-    if use_ref:
-        mk = lambda: refbind.RefSource(dict(SETTINGS), impl=refbind.IMPL_AVX2, channels=1)
-        desc = "oracle/_ref: WAVSourceAVX2::tick_spectrum + vendored FFTW 3.3.11 (AVX2 codelets)"
+    if refbind.available():
+        which = refbind.IMPL_AVX2 if impl == "avx2" else refbind.IMPL_GENERIC
+        mk = lambda: refbind.RefSource(dict(SETTINGS), impl=which, channels=1)
+        desc = ("oracle/_ref: WAVSourceAVX2::tick_spectrum" if impl == "avx2" else "oracle/_ref: WAVSourceGeneric::tick_spectrum") \
+            + " + vendored FFTW 3.3.11 (AVX2 codelets)"
     else:
         from oracle import oraclebind
         kind = "port"
@@ -108,7 +119,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
+    cores = len(ALL_CPUS)
     per_thread = 8192
     vals = []
     for _ in range(args.warmup):
@@ -128,7 +139,8 @@ def run_reference_arm(args):
         "config": {"workload": workload_name(), "fft_size": N_FFT, "frames_per_step": frames_per_step,
                    "note": "CPU arm: bounded sample of the same workload per step, all host threads"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                         "sample": f"{frames_per_step} frames/step ({info['desc']}), hop=N, data cache-resident"},
+                         "sample": f"{frames_per_step} frames/step ({info['desc']}), hop=N, data cache-resident",
+                         "affinity_cpus": cores, "os_cpu_count": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -205,7 +217,7 @@ def make_pcm_on_device(torch, S, T, device, seed):
     c = torch.arange(S, device=device, dtype=torch.float32)
     fc = 110.0 * torch.pow(2.0, torch.remainder(c, 60.0) / 12.0)
     pcm = torch.empty((S, 1, ns), device=device, dtype=torch.float32)
-    chunk = 512
+    chunk = max(1, (1 << 24) // ns)
     for s0 in range(0, S, chunk):
         s1 = min(S, s0 + chunk)
         ph = 2.0 * torch.pi * fc[s0:s1, None] * n[None, :] / 48000.0
@@ -217,17 +229,154 @@ def make_pcm_on_device(torch, S, T, device, seed):
     return pcm
 
 
+def time_steps(torch, stream, step, steps, warmup):
+    """CUDA-event time per step (ms) of `step()` launched on `stream`: list of per-step times."""
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record(stream)
+    for k in range(steps):
+        step()
+        evs[k + 1].record(stream)
+    torch.cuda.synchronize()
+    return [evs[k].elapsed_time(evs[k + 1]) for k in range(steps)]
+
+
+def parity_subset(torch, device, pcm, S, T):
+    """run the MEASURED launch geometry once from a fresh state and compare the first 256 frames of the
+    shard plus streams from the far ends of the grid with the reference's generic CPU path (oracle/_ref; the C port if
+    the compiled reference is absent).  Criterion = tests/helpers.py::parity_report (DESIGN.md §2)."""
+    import numpy as np
+
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import parity_report
+    from oracle import refbind
+    from waveform_b200 import Engine
+
+    eng = Engine(dict(SETTINGS), channels=1, max_streams=S, device=device.index)
+    out = eng.process(pcm, T, N_FFT)
+    torch.cuda.synchronize()
+    kernel = eng.last_kernel_name()
+    n_first = max(1, min(S, -(-256 // T)))
+    pick = sorted(set(range(n_first)) | {S - 1, S - 2, S // 2, S // 3, 147 % S, 148 % S, (148 * 16) % S, (148 * 16 + 147) % S,
+                                         (148 * 27) % S} | set(range(0, S, max(1, S // 40))))
+    idx = torch.tensor(pick, device=device)
+    got = out["db"][idx].cpu().numpy()
+    got_sil = out["silent"][idx].cpu().numpy()
+    rows = pcm[idx].cpu().numpy()
+    if refbind.available():
+        mk = lambda: refbind.RefSource(dict(SETTINGS), impl=refbind.IMPL_GENERIC, channels=1)
+        against = "oracle/_ref WAVSourceGeneric::tick_spectrum (the unmodified reference, compiled)"
+    else:
+        from oracle import oraclebind
+        mk = lambda: oraclebind.OracleSource(dict(SETTINGS), channels=1)
+        against = "oracle/liboracle.so (C restatement of source_generic.cpp)"
+    ref, ref_sil = [], []
+    for r in rows:
+        o = mk().run_stft(r, T, N_FFT)
+        ref.append(o["db"])
+        ref_sil.append(o["silent"])
+    ref, ref_sil = np.stack(ref), np.stack(ref_sil)
+    rep = parity_report(got, ref, db_min=eng.db_min)
+    return {"ok": bool(rep["ok"] and rep["normwise"] < 1e-6 and np.array_equal(got_sil, ref_sil)),
+            "streams_checked": len(pick), "frames_checked": len(pick) * T, "normwise": rep["normwise"],
+            "frac_bins_within_1e-5_rel": rep["frac_rel_1e5"], "max_db_err_strong_bins": rep["max_db_strong"],
+            "silent_flags_equal": bool(np.array_equal(got_sil, ref_sil)), "silent_ticks_in_sample": int(ref_sil.sum()),
+            "kernel": kernel, "against": against,
+            "criterion": "|gpu-ref| <= 1e-5|ref| + 1e-6 frame_peak (linear), normwise < 1e-6, identical DB_MIN pattern and silent flags"}
+
+
+def run_layouts(torch, device, stream, peak_gbs, steps):
+    """The same 65 536-frame batch in every streams x frames factorisation of SURVEY §8(d) C3."""
+    from waveform_b200 import Engine
+
+    res = []
+    out = torch.empty((65536, 1, BINS), device=device, dtype=torch.float32)
+    for (S, T) in LAYOUTS:
+        eng = Engine(dict(SETTINGS), channels=1, max_streams=S, device=device.index)
+        pcm = make_pcm_on_device(torch, S, T, device, seed=0xB200)
+        step = lambda: eng.process_raw(pcm.data_ptr(), S, T, N_FFT, T * N_FFT, T * N_FFT, out_db=out.data_ptr(),
+                                       stream=stream.cuda_stream, sync=False)
+        ms = statistics.mean(time_steps(torch, stream, step, steps, 3))
+        gbs = 65536 * BYTES_PER_FRAME / (ms * 1e-3) / 1e9
+        with_state = (65536 * BYTES_PER_FRAME + S * STATE_BYTES_PER_STREAM) / (ms * 1e-3) / 1e9
+        res.append({"streams": S, "frames": T, "value": 65536 / (ms * 1e-3), "kernel_ms": ms, "frac": gbs / peak_gbs,
+                    "frac_incl_state_bytes": with_state / peak_gbs, "kernel": eng.last_kernel_name()})
+        del eng, pcm
+    return res
+
+
+def run_c5(torch, dist, device, world, steps):
+    """BASELINE.json configs[4]: N=16384, 128 streams x 256 ticks per GPU (262 144 frames over 8 GPUs), cross-GPU peak
+    normalisation: kernel (with the per-tick peak) -> NCCL all_reduce(MAX) of 256 floats -> normalise pass, all inside the
+    timed loop and on one stream.  Value = frames of all ranks / max-over-ranks device time."""
+    from waveform_b200 import Engine
+    from waveform_b200.shard import ShardedEngine
+
+    N, S, T = 16384, 128, 256
+    eng = Engine({"fft_size": N, "window": "hann"}, channels=1, max_streams=S, device=device.index)
+    sh = ShardedEngine(eng)
+    g = torch.Generator(device=device)
+    g.manual_seed(0xC5 + int(os.environ.get("RANK", "0")))
+    pcm = (torch.rand((S, 1, T * N), device=device, generator=g) - 0.5) * (0.1 + 0.05 * int(os.environ.get("RANK", "0")))
+    # correctness of the exchange on the measured shape: all-reduced peak == max of the local peaks, output == local + gain
+    plain = eng.process(pcm, T, N, want_peak=True)
+    local_peak = plain["peak"].clone()
+    local_db = plain["db"].clone()
+    del plain
+    eng2 = Engine({"fft_size": N, "window": "hann"}, channels=1, max_streams=S, device=device.index)
+    out = ShardedEngine(eng2).process_normalized(pcm, T, N, target_db=-3.0, max_gain=30.0)
+    if world > 1:
+        allp = [torch.empty_like(local_peak) for _ in range(world)]
+        dist.all_gather(allp, local_peak)
+        want = torch.stack(allp).max(dim=0).values
+    else:
+        want = local_peak
+    gain = torch.clamp(-3.0 - want, max=30.0)
+    local_db[..., 1:] += gain[None, :, None, None]
+    ok = bool(torch.equal(out["peak"], want) and torch.equal(out["db"], local_db))
+    del out, local_db, eng2
+    torch.cuda.empty_cache()
+    for _ in range(2):
+        sh.process_normalized(pcm, T, N)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sh.process_normalized(pcm, T, N)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    frames = S * T * world
+    bytes_per_frame = N * 4 + (N // 2) * 4
+    return {"workload": f"c5: N=16384 Hann, {S} streams x {T} ticks per GPU ({frames} frames total), per-tick peak -> "
+                        f"{'NCCL all_reduce(MAX) of ' + str(T) + ' floats' if world > 1 else 'no exchange (1 GPU)'} -> normalise pass",
+            "value": frames / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "frac_per_gpu": (S * T * bytes_per_frame / (ms * 1e-3) / 1e9) / load_peaks()[0],
+            "exchange_exact": ok, "kernel": eng.last_kernel_name()}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
     from waveform_b200 import Engine
+    from waveform_b200.hostbind import bind_to_gpu_node
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    # NUMA: pin this rank to its GPU's node BEFORE any pinned buffer exists (first touch decides where the pages live)
+    numa = bind_to_gpu_node(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -252,6 +401,12 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     props = torch.cuda.get_device_properties(device)
     gpu_id = "GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank)
     sampler = ClockSampler(gpu_id) if rank == 0 else None
@@ -270,15 +425,33 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     launches = eng.launch_count - launches0
+    kernel_name = eng.last_kernel_name()
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
     clocks = sampler.stop(t_begin, t_end) if sampler else None
-    tmax = torch.tensor([total_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
-    ms_per_step = total_ms_max / args.steps
+    ms_per_step = max_over_ranks(total_ms) / args.steps
     value = frames_per_gpu * world / (ms_per_step * 1e-3)
+
+    # ---- strong scaling: the literal "batch = 65536" split over the N GPUs (4096/N streams x 16 frames per GPU) ----
+    strong = None
+    if world > 1:
+        Ss = max(1, S // world)
+        steps_s = min(args.steps, 50)
+        step_s = lambda: eng.process_raw(pcm.data_ptr(), Ss, T, N_FFT, T * N_FFT, T * N_FFT, out_db=out.data_ptr(),
+                                         stream=stream.cuda_stream, sync=False)
+        for _ in range(3):
+            step_s()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps_s):
+            step_s()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_s = max_over_ranks(e0.elapsed_time(e1)) / steps_s
+        strong = {"value": Ss * T * world / (ms_s * 1e-3), "unit": UNIT, "frames_total": Ss * T * world,
+                  "streams_per_gpu": Ss, "ms_per_step": ms_s, "scaling": "strong",
+                  "note": "65 536 frames TOTAL per step; per-GPU launches shrink with N (launch-latency territory at N=8)"}
 
     # ---- end-to-end: host (pinned) buffers through the C-ABI, H2D + kernel + D2H inside the timed region ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -290,6 +463,21 @@ def run_gpu_arm(args):
         eng.process_raw(h_pcm.data_ptr(), S, T, N_FFT, T * N_FFT, T * N_FFT, out_db=h_out.data_ptr(),
                         stream=stream.cuda_stream, sync=False)
 
+    # the host ceiling of this rank, measured: a bare pinned H2D copy of the same bytes (no kernel, no D2H)
+    d_probe = torch.empty_like(pcm)
+    with torch.cuda.stream(stream):
+        d_probe.copy_(h_pcm, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            d_probe.copy_(h_pcm, non_blocking=True)
+    c1.record(stream)
+    torch.cuda.synchronize()
+    h2d_gbs_alone = 3 * h_pcm.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del d_probe
+
     step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -298,24 +486,56 @@ def run_gpu_arm(args):
         step_e2e()
     e1.record(stream)
     torch.cuda.synchronize()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = frames_per_gpu * world / (float(e2e_ms.item()) * 1e-3 / e2e_steps)
+    e2e_rank_ms = e0.elapsed_time(e1) / e2e_steps
+    e2e_ms = max_over_ranks(e2e_rank_ms)
+    e2e_value = frames_per_gpu * world / (e2e_ms * 1e-3)
     checksum = float(h_out[:: max(1, S // 64)].double().sum())  # host read of the step's result
+    h2d_rank = torch.tensor([h_pcm.numel() * 4 / (e2e_rank_ms * 1e-3) / 1e9, h2d_gbs_alone], device=device, dtype=torch.float64)
+    if world > 1:
+        allr = [torch.empty_like(h2d_rank) for _ in range(world)]
+        dist.all_gather(allr, h2d_rank)
+        h2d_all = torch.stack(allr).cpu().tolist()
+        numa_all = [None] * world
+        dist.all_gather_object(numa_all, numa)
+    else:
+        h2d_all, numa_all = [h2d_rank.cpu().tolist()], [numa]
+    del h_pcm, h_out
+
+    # ---- parity of the measured launch geometry (after the timed regions) ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_subset(torch, device, pcm, S, T)
+
+    # ---- config 5 with its collective (every N; N=1 has no exchange) ----
+    c5 = None
+    if not args.no_c5:
+        del out
+        torch.cuda.empty_cache()
+        c5 = run_c5(torch, dist, device, world, steps=5)
+        out = torch.empty((S, T, 1, BINS), device=device, dtype=torch.float32)
 
     if rank == 0:
         peak_gbs, peak_src = load_peaks()
         traffic, traffic_src = load_traffic() if (S, T) == (4096, 16) else (None, None)
         kernel_ms = statistics.mean(per_launch)
         achieved = frames_per_gpu * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+        layouts = None
+        if world == 1 and not args.no_layouts:
+            layouts = run_layouts(torch, device, stream, peak_gbs, steps=20)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            os.sched_setaffinity(0, ALL_CPUS)  # the CPU arm uses every core the box grants, not just the GPU's NUMA node
+            cores = len(ALL_CPUS)
             v, info = cpu_reference_throughput(args.cpu_frames_per_thread, cores)
+            v1, i1 = cpu_reference_throughput(32768, 1)
+            vg, ig = cpu_reference_throughput(16384, 1, impl="generic")
             cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                    "sample": f"{info['frames']} frames in {info['seconds']:.2f}s wall ({info['desc']}), hop=N, "
-                             "same N=2048 Hann EMA dBFS settings, data cache-resident"}
+                             "same N=2048 Hann EMA dBFS settings, data cache-resident",
+                   "affinity_cpus": cores, "os_cpu_count": os.cpu_count(),
+                   "avx2_1core": {"value": v1, "unit": UNIT, "cores": 1, "sample": f"{i1['frames']} frames in {i1['seconds']:.2f}s"},
+                   "generic_1core": {"value": vg, "unit": UNIT, "cores": 1,
+                                     "sample": f"{ig['frames']} frames in {ig['seconds']:.2f}s ({ig['desc']}; the parity target)"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -323,16 +543,20 @@ def run_gpu_arm(args):
             "config": {"workload": workload_name(), "fft_size": N_FFT, "streams_per_gpu": S, "frames_per_stream": T,
                        "hop": N_FFT, "frames_per_step_per_gpu": frames_per_gpu,
                        "l2_policy": "inputs 512 MiB + outputs 256 MiB per step exceed the 126 MB L2 (no flush needed)",
-                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                       "extra": {"layouts_same_batch": layouts, "strong_scaling": strong, "c5": c5}},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_pcm.numel() * 4),
-                    "d2h_bytes_per_step": int(h_out.numel() * 4), "steps": e2e_steps, "checksum": checksum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * T * N_FFT * 4),
+                    "d2h_bytes_per_step": int(S * T * BINS * 4), "steps": e2e_steps, "checksum": checksum,
+                    "per_gpu_h2d_gbs_in_e2e": [round(r[0], 2) for r in h2d_all],
+                    "per_gpu_h2d_gbs_copy_alone": [round(r[1], 2) for r in h2d_all],
+                    "numa_binding": numa_all},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src,
-                         "kernel": "stft2048_fast_kernel<16,true,true,false> (csrc/wf_fast2048.cuh)", "kernel_ms": kernel_ms,
+                         "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "bytes_per_launch": frames_per_gpu * BYTES_PER_FRAME},
+            "parity": parity,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -353,6 +577,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-frames-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-layouts", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -206,6 +206,10 @@ int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_fr
 
 /* Number of kernel launches this engine has issued (bench.py reports it as gpu_launches). */
 int64_t wf_launch_count(const wf_engine *e);
+/* Name (template arguments and launch geometry included) of the spectrum kernel the most recent wf_process* call
+ * dispatched to, e.g. "stft2048_fast_kernel<16,1,1,0> grid 148 x 14 warps"; "" before the first call.  Valid until the
+ * next call on this engine.  bench.py reports it as roofline.kernel, the tests assert the routing with it. */
+const char *wf_last_kernel_name(const wf_engine *e);
 /* Device time (ms) of the kernel section of the most recent wf_process / wf_process_async / wf_peak_normalize call,
  * measured with CUDA events on the launching stream; < 0 if none. Synchronises on the recorded events. */
 float wf_last_kernel_ms(wf_engine *e);

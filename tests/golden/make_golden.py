@@ -134,11 +134,62 @@ def main_wave():
         print("wave", name, r["out"].shape, "silent ticks", int(r["silent"].sum()))
 
 
+# "Not enough audio" (src/source_generic.cpp:55-61): the only way the plugin's public API produces it is audio that is
+# stamped AHEAD of the tick clock (positive get_audio_sync, src/source.hpp:279-285): the tick then wants delay + N samples
+# and the ring, trimmed to N by the earlier in-sync packets, needs a few ticks to refill.  During those ticks the channel
+# `continue`s while m_last_silent is false, so the stale dB values are pushed through dbfs() again.
+# The fixture stores the sample stream the ticks see (`pcm`, with the N start-up zeros update() leaves in the ring) and,
+# per engine call, the offset of frame 0, the number of ticks and the skip mask; frame t of a call = pcm[offset + t*hop ...+N).
+STALL_CASES = {
+    "2048_avsync_jump": dict(settings={"fft_size": 2048, "window": "hann"}, channels=1, T=14, hop=800, jump_at=5,
+                             ahead_ms=50),
+    "1024_stereo_jump_rolloff": dict(settings={"fft_size": 1024, "window": "hamming", "channel_mode": "stereo",
+                                               "rolloff_q": 1.0, "rolloff_rate": 6.0}, channels=2, T=16, hop=512,
+                                     jump_at=6, ahead_ms=32),
+}
+
+
+def main_stall():
+    for name, c in STALL_CASES.items():
+        ref = RefSource(c["settings"], impl=IMPL_GENERIC, channels=c["channels"])
+        N, T, hop, J = ref.fft_size, c["T"], c["hop"], c["jump_at"]
+        cc = ref.capture_channels
+        audio = synth_pcm(1, cc, T * hop, seed=0xB200 + len(name))[0]
+        delay = int(round(c["ahead_ms"] * 1e-3 * 48000))
+        assert delay % hop == 0, "keep the delayed frames on the hop grid"
+        dbs, sil = [], []
+        for t in range(T):
+            ref.advance(hop / 48000.0)
+            ref.push(audio[0, t * hop:(t + 1) * hop], audio[1, t * hop:(t + 1) * hop] if cc > 1 else None,
+                     ts_adjust_ns=0 if t < J else int(c["ahead_ms"] * 1e6))
+            ref.tick(1.0 / 60.0)
+            dbs.append(np.stack([ref.decibels(ch) for ch in range(ref.display_channels)]))
+            sil.append(ref.last_silent)
+        db = np.stack(dbs)
+        # what the ticks saw: ring = [N zeros][audio]; in sync, tick t takes the newest N samples = ring[(t+1)*hop ...);
+        # delayed, the oldest N of the newest delay+N = ring[(t+1)*hop - delay ...), once the ring holds that much
+        ring = np.concatenate([np.zeros((cc, N), np.float32), audio], axis=1)
+        k = delay // hop
+        calls = [dict(offset=hop, n_frames=J, skip=[0] * J),
+                 dict(offset=(J + 1 - k) * hop, n_frames=T - J, skip=[1] * (k - 1) + [0] * (T - J - k + 1))]
+        skipped = [t for t in range(J, J + k - 1)]  # the first delayed push already counts towards the refill
+        assert all((db[t] <= ref.db_min + 1).all() for t in skipped) and (db[J + k - 1] > ref.db_min + 1).any()
+        np.savez_compressed(OUT / f"stall_{name}.npz", settings=json.dumps(c["settings"]), channels=c["channels"], hop=hop,
+                            n_frames=T, seconds=1.0 / 60.0, pcm=ring, calls=json.dumps(calls), db=db,
+                            silent=np.array(sil, np.uint8), db_min=np.float32(ref.db_min))
+        print("stall", name, "N", N, "skipped ticks", skipped, "db at first skipped tick: max", float(db[J].max()))
+
+
 if __name__ == "__main__":
     import sys
+    if "--stall-only" in sys.argv:
+        main_stall()
+        sys.exit(0)
     if "--meter-only" not in sys.argv and "--wave-only" not in sys.argv:
         main()
     if "--wave-only" not in sys.argv:
         main_meter()
     if "--meter-only" not in sys.argv:
         main_wave()
+    if "--meter-only" not in sys.argv and "--wave-only" not in sys.argv:
+        main_stall()

@@ -70,3 +70,53 @@ def check_points(settings, channels, got_db, got_points):
     d = np.abs(np.asarray(got_points, dtype=np.float64) - exp.astype(np.float64))
     scale = np.maximum(np.abs(exp).max(axis=-1, keepdims=True), 1.0)
     return float((d / scale).max())
+
+
+def device_pcm(n_streams: int, channels: int, n_samples: int, seed: int = 0xB200, zero_every: int = 0, frame_len: int = 0):
+    """The same signal family generated ON THE DEVICE (torch) for shapes too large for synth_pcm: noise + two sines per
+    (stream, channel); with zero_every > 0 every zero_every-th aligned block of frame_len samples of a stream-dependent
+    phase is digital silence, so that the silence gate runs at scale.  Returns a CUDA tensor [S, cc, ns]."""
+    import torch
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n = torch.arange(n_samples, device=dev, dtype=torch.float32)
+    pcm = torch.empty((n_streams, channels, n_samples), device=dev, dtype=torch.float32)
+    rows = n_streams * channels
+    flat = pcm.view(rows, n_samples)
+    chunk = max(1, (1 << 26) // max(1, n_samples))
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        idx = torch.arange(r0, r1, device=dev, dtype=torch.float32)
+        fc = 110.0 * torch.pow(2.0, torch.remainder(idx, 60.0) / 12.0)
+        ph = 2.0 * torch.pi * fc[:, None] * n[None, :] / SR
+        x = 0.25 * (2.0 * torch.rand((r1 - r0, n_samples), device=dev, generator=g) - 1.0)
+        x += 0.5 * torch.sin(ph) + 0.1 * torch.sin(3.01 * ph)
+        flat[r0:r1] = x
+    if zero_every > 0 and frame_len > 0:
+        nb = n_samples // frame_len
+        blk = pcm[:, :, : nb * frame_len].view(n_streams, channels, nb, frame_len)
+        s = torch.arange(n_streams, device=dev)[:, None]
+        b = torch.arange(nb, device=dev)[None, :]
+        zero = ((b + 3 * s) % zero_every) == 0          # [S, nb]
+        blk[zero[:, None, :].expand(n_streams, channels, nb)] = 0.0
+    return pcm
+
+
+def fp64_truth_db(pcm, window, window_sum, n_frames, hop, g, db_min=-758.59564):
+    """Double-precision ground truth of the plain pipeline (window -> DFT -> |X| 2/sum(w) -> EMA -> dBFS) for one mono
+    stream, from the SAME float32 window table (so that only the arithmetic differs): SURVEY.md §7 'both
+    implementations' error vs fp64 truth'.  pcm: [samples] float32."""
+    N = len(window)
+    w = window.astype(np.float64)
+    coef = 2.0 / float(window_sum)
+    state = np.zeros(N // 2)
+    out = np.empty((n_frames, N // 2))
+    for t in range(n_frames):
+        x = pcm[t * hop: t * hop + N].astype(np.float64) * w
+        mag = np.abs(np.fft.rfft(x)[: N // 2]) * coef
+        state = g * state + (1.0 - g) * mag
+        with np.errstate(divide="ignore"):
+            out[t] = np.where(state > 0, 20.0 * np.log10(np.maximum(state, 1e-300)), db_min)
+    return out

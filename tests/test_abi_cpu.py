@@ -152,3 +152,23 @@ def test_meter_and_wave_fail_loudly_without_a_gpu_and_reject_bad_configs():
         with pytest.raises(WfError) as ei:
             ctor()
         assert ei.value.status == -4 and "no CPU fallback" in str(ei.value)
+
+
+def test_hostbind_parses_sysfs(tmp_path):
+    """NUMA placement helper used by bench.py's end-to-end leg: sysfs parsing only (no GPU, no affinity change)."""
+    from waveform_b200 import hostbind
+
+    assert hostbind.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert hostbind.parse_cpulist("") == []
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices" / "system" / "node" / "node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("32-63,96-127\n")
+    assert hostbind.numa_node_of_pci("0000:1b:00.0", sysfs=str(tmp_path)) == 1
+    assert len(hostbind.cpus_of_node(1, sysfs=str(tmp_path))) == 64
+    (dev / "numa_node").write_text("-1\n")
+    assert hostbind.numa_node_of_pci("0000:1b:00.0", sysfs=str(tmp_path)) is None
+    info = hostbind.bind_to_gpu_node(0, sysfs=str(tmp_path))   # no CUDA device here: reports why, never raises
+    assert info["bound"] is False and info["why"]

@@ -1,0 +1,245 @@
+"""GPU parity at the launch geometries that are actually MEASURED (bench.py, tools/bench_shapes.py), not toy shapes.
+
+The small-shape tests (test_gpu_parity.py) run 1-37 streams, which the N=2048 warp-per-stream kernel maps to one warp
+per CTA and one round.  The headline launch is 148 CTAs x 16 warps x 2 rounds with SM-interleaved stream indices and
+next-stream TMA prefetch; the CTA-per-tick kernel picks its cluster size from the stream count.  These tests run the
+real geometries on the device and compare a strided sample of streams (first / last warp of several CTAs, every round,
+plus random ones: >= 64 streams) against the oracle, and every stream against a cheap whole-batch invariant.
+
+Run on a B200:  python -m pytest tests -m gpu -x -q
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import check_points, device_pcm, fp64_truth_db, parity_report, synth_pcm
+
+pytestmark = pytest.mark.gpu
+
+SMS = 148
+
+
+def _sample_streams(S: int, n_random: int = 40, seed: int = 1) -> list[int]:
+    """Streams at the corners of the N=2048 kernel's decomposition (stream s -> CTA s % 148, local index s // 148,
+    warp = local % 16, round = local // 16) + the first/last few + random ones."""
+    per_cta = (S + SMS - 1) // SMS
+    locals_ = sorted({0, 1, 15, 16, 17, per_cta - 2, per_cta - 1} & set(range(per_cta)))
+    ctas = [0, 1, 2, 73, 74, 146, 147]
+    pick = {c + li * SMS for li in locals_ for c in ctas}
+    pick |= {0, 1, 2, S - 1, S - 2, S // 2}
+    rng = np.random.default_rng(seed)
+    pick |= set(int(x) for x in rng.integers(0, S, n_random))
+    return sorted(s for s in pick if 0 <= s < S)
+
+
+def _oracle_rows(settings, channels, pcm_rows, T, hop, want_points=False):
+    from oracle.oraclebind import OracleSource
+
+    db, pts, sil = [], [], []
+    for row in pcm_rows:
+        r = OracleSource(settings, channels=channels).run_stft(row, T, hop, want_points=want_points)
+        db.append(r["db"])
+        pts.append(r["points"])
+        sil.append(r["silent"])
+    return np.stack(db), (np.stack(pts) if want_points else None), np.stack(sil)
+
+
+def _run_and_check(settings, channels, S, T, hop_div=1, zero_every=7, want_points=False, n_random=40, calls=1):
+    import torch
+    from waveform_b200 import Engine
+
+    eng = Engine(settings, channels=channels, max_streams=S)
+    N, cc = eng.fft_size, eng.capture_channels
+    hop = N // hop_div
+    ns = (T - 1) * hop + N
+    pcm = device_pcm(S, cc, ns, seed=0xB200 + S + T, zero_every=zero_every, frame_len=hop)
+    if calls == 1:
+        out = eng.process(pcm, T, hop, want_points=want_points)
+    else:  # the same ticks in `calls` consecutive launches: state, hold and flags cross the call boundary
+        parts, t0 = [], 0
+        for c in range(calls):
+            n = T // calls + (1 if c < T % calls else 0)
+            parts.append(eng.process(pcm[:, :, t0 * hop:].contiguous(), n, hop, want_points=want_points))
+            t0 += n
+        out = {k: torch.cat([p[k] for p in parts], dim=1) for k in parts[0]}
+    torch.cuda.synchronize()
+    pick = _sample_streams(S, n_random=n_random)
+    assert len(pick) >= min(S, 48)
+    idx = torch.tensor(pick, device="cuda")
+    got_db = out["db"][idx].cpu().numpy()
+    got_sil = out["silent"][idx].cpu().numpy()
+    ref_db, ref_pts, ref_sil = _oracle_rows(settings, channels, pcm[idx].cpu().numpy(), T, hop, want_points=want_points)
+    rep = parity_report(got_db, ref_db, db_min=eng.db_min)
+    assert rep["ok"] and rep["normwise"] < 1e-6, rep
+    assert np.array_equal(got_sil, ref_sil)
+    if want_points:
+        gp = out["points"][idx].cpu().numpy()
+        assert check_points(settings, channels, got_db, gp) < 2e-6
+        d = np.abs(gp.astype(np.float64) - ref_pts.astype(np.float64))
+        assert np.median(d) < 1e-4 and np.nanmax(d) < 2e-2
+    # whole-batch invariants over EVERY stream (cheap, size independent): finite, >= DB_MIN, and no stream left unwritten
+    db = out["db"]
+    assert bool(torch.isfinite(db).all()) and float(db.min()) >= eng.db_min - 1e-3
+    row_max = db.amax(dim=(1, 2, 3))
+    assert float(row_max.min()) > -200.0, "a stream's outputs were never written"
+    return eng, out, pcm
+
+
+FAST_SHAPES = [
+    # (S, T, calls): 300 -> 3 warps/CTA; 2500 -> 16 warps + a ragged second round; 4096x16 = the bench launch;
+    # 65536x1 and 1024x64 = two more layouts of profiles/r0x_layouts.txt; 2369 -> one stream more than 148 x 16
+    (300, 9, 1), (2500, 5, 2), (4096, 16, 1), (2369, 3, 1), (65536, 1, 1), (1024, 40, 2), (768, 33, 3),
+]
+
+
+@pytest.mark.parametrize("S,T,calls", FAST_SHAPES)
+def test_fast2048_parity_at_measured_geometry(S, T, calls):
+    settings = {"fft_size": 2048, "window": "hann", "gravity": 0.65}
+    eng, out, _ = _run_and_check(settings, 1, S, T, calls=calls)
+    assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+
+
+@pytest.mark.parametrize("S,T", [(256, 64), (512, 48), (148, 40)])
+def test_n2048_few_streams_many_ticks(S, T):
+    """Few streams x many ticks (SURVEY §8(d) C3 '256 x 256' family): whatever kernel the engine routes this to, parity holds."""
+    settings = {"fft_size": 2048, "window": "hann", "gravity": 0.65}
+    _run_and_check(settings, 1, S, T, calls=2)
+
+
+V3_SHAPES = [
+    # (settings, channels, S, T, hop_div, want_points)
+    ({"fft_size": 4096, "window": "hann"}, 1, 1024, 4, 1, False),
+    ({"fft_size": 4096, "window": "blackman_harris", "channel_mode": "stereo"}, 2, 1100, 6, 4, False),   # config 2 at scale
+    ({"fft_size": 2048, "window": "hann", "channel_mode": "stereo"}, 2, 1200, 3, 1, False),
+    ({"fft_size": 8192, "window": "hann", "interp_mode": "lanczos"}, 1, 256, 16, 4, True),               # config 4 shape
+    ({"fft_size": 8192, "window": "hann"}, 1, 1024, 3, 1, False),
+    ({"fft_size": 16384, "window": "hann"}, 1, 128, 12, 1, False),                                       # config 5 shape (per GPU)
+    ({"fft_size": 1024, "window": "hann", "display_mode": "bars", "interp_mode": "catmull_rom"}, 1, 2048, 4, 1, True),
+    ({"fft_size": 800, "window": "hann"}, 1, 1500, 4, 1, False),                                         # the automatic size
+    ({"fft_size": 1920, "window": "blackman"}, 1, 600, 4, 2, False),
+]
+
+
+@pytest.mark.parametrize("settings,channels,S,T,hop_div,want_points", V3_SHAPES)
+def test_other_kernels_parity_at_scale(settings, channels, S, T, hop_div, want_points):
+    """>= 1024 streams (cluster size 1) and few-stream shapes (clusters of 2-8 CTAs per stream) of the CTA-per-tick
+    kernel, the stereo path, display epilogues and the mixed-radix sizes, all at real stream counts."""
+    _run_and_check(settings, channels, S, T, hop_div=hop_div, want_points=want_points, n_random=24, calls=2)
+
+
+GOLD = sorted((Path(__file__).parent / "golden").glob("case_*.npz"))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
+def test_golden_vectors_spectrum_only(path):
+    """The reference's golden vectors WITHOUT display outputs: for case_c3_mono_2048_hann this is the headline
+    stft2048_fast_kernel (the display-points variant of this test in test_gpu_parity.py routes to the CTA-per-tick kernel)."""
+    z = np.load(path, allow_pickle=False)
+    settings = json.loads(str(z["settings"]))
+    from waveform_b200 import Engine
+
+    eng = Engine(settings, channels=int(z["channels"]), max_streams=1)
+    rms = z["rms"][None, :] if z["rms"].size else None
+    out = eng.process(z["pcm"][None], int(z["n_frames"]), int(z["hop"]), seconds=float(z["seconds"]), input_rms=rms)
+    rep = parity_report(out["db"][0], z["db"], db_min=float(z["db_min"]))
+    assert rep["ok"] and rep["normwise"] < 1e-6, rep
+    assert np.array_equal(out["silent"][0], z["silent"])
+    if path.stem == "case_c3_mono_2048_hann":
+        assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+
+
+@pytest.mark.parametrize("split", [None, 7, 12])
+def test_fast2048_gate_decay_freeze_wake(split):
+    """Decay -> freeze -> wake-up on the warp-per-stream kernel (T < 32 keeps N=2048 mono on it), with the call boundary
+    inside the decay (7) and inside the frozen stretch (12): the next call must see the held dB row and both gate flags."""
+    settings = {"fft_size": 2048, "window": "hann", "gravity": 0.3, "floor": -40}
+    S, T, N = 5, 30, 2048
+    pcm = synth_pcm(S, 1, T * N)
+    pcm[:, :, 4 * N:] = 0.0
+    pcm[2, :, 20 * N: 22 * N] = 0.1   # wakes up again
+    pcm[4, :, 9 * N: 10 * N] = 0.2    # wakes up while still decaying
+    from waveform_b200 import Engine
+
+    eng = Engine(settings, channels=1, max_streams=S)
+    if split is None:
+        out = eng.process(pcm, T, N)
+    else:
+        a = eng.process(pcm[:, :, : split * N], split, N)
+        b = eng.process(pcm[:, :, split * N:], T - split, N)
+        out = {k: np.concatenate([a[k], b[k]], axis=1) for k in ("db", "silent")}
+    assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+    ref_db, _, ref_sil = _oracle_rows(settings, 1, pcm, T, N)
+    assert ref_sil.sum() > 10 and ref_sil[2, 21] == 0 and ref_sil[2, -1] == 1, "test must exercise freeze and wake-up"
+    assert np.array_equal(out["silent"], ref_sil)
+    rep = parity_report(out["db"], ref_db, db_min=eng.db_min)
+    assert rep["ok"], rep
+    s, t = np.argwhere(ref_sil == 1)[3]
+    assert np.array_equal(out["db"][s, t], out["db"][s, t - 1])  # held rows are bit-identical copies
+
+
+STALL = sorted((Path(__file__).parent / "golden").glob("stall_*.npz"))
+
+
+@pytest.mark.parametrize("device_ptrs", [False, True])
+@pytest.mark.parametrize("path", STALL, ids=[p.stem for p in STALL])
+def test_skip_mask_against_reference_not_enough_audio(path, device_ptrs):
+    """A real, non-zero skip_mask: the ticks on which the compiled reference had 'not enough audio'
+    (src/source_generic.cpp:55-61; fixtures from tests/golden/make_golden.py --stall-only).  While a channel is skipped
+    with m_last_silent == false the reference pushes the stale dB values through dbfs() again (:138-159)."""
+    import torch
+    from test_oracle_golden import stall_calls
+    from waveform_b200 import Engine
+
+    z = np.load(path, allow_pickle=False)
+    settings = json.loads(str(z["settings"]))
+    eng = Engine(settings, channels=int(z["channels"]), max_streams=3)
+    hop = int(z["hop"])
+    dbs, sils = [], []
+    for pcm, n, skip in stall_calls(z):
+        # three streams: 0 and 2 follow the fixture, stream 1 is never skipped (the mask is per stream and tick)
+        batch = np.ascontiguousarray(np.stack([pcm, pcm, pcm]))
+        mask = np.stack([skip, np.zeros_like(skip), skip])
+        if device_ptrs:
+            out = eng.process(torch.from_numpy(batch).cuda(), n, hop, seconds=float(z["seconds"]),
+                              skip_mask=torch.from_numpy(mask).cuda())
+            torch.cuda.synchronize()
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        else:
+            out = eng.process(batch, n, hop, seconds=float(z["seconds"]), skip_mask=mask)
+        dbs.append(out["db"])
+        sils.append(out["silent"])
+    db, sil = np.concatenate(dbs, axis=1), np.concatenate(sils, axis=1)
+    skipped = np.concatenate([s for _, _, s in stall_calls(z)]).astype(bool)
+    assert skipped.sum() >= 2
+    for s in (0, 2):
+        rep = parity_report(db[s], z["db"], db_min=float(z["db_min"]))
+        assert rep["ok"] and rep["normwise"] < 1e-6, (s, rep)
+        assert np.array_equal(sil[s], z["silent"])
+        assert (db[s][skipped] <= float(z["db_min"]) + 1e-3).all()      # stale dB -> dbfs() -> DB_MIN
+    assert (db[1][skipped].max(axis=(-1, -2)) > -100).all()             # the unmasked stream kept going
+
+
+def test_fp64_arbiter_gpu_and_reference_errors():
+    """both implementations' error against a double-precision ground truth.  The CUDA path must be as
+    close to the truth as the reference's own FFTW path is (both are fp32 FFTs; normwise ~1e-7), on the golden PCM."""
+    z = np.load(Path(__file__).parent / "golden" / "case_c3_mono_2048_hann.npz", allow_pickle=False)
+    settings = json.loads(str(z["settings"]))
+    from waveform_b200 import Engine
+
+    T, hop = int(z["n_frames"]), int(z["hop"])
+    eng = Engine(settings, channels=1, max_streams=1)
+    got = eng.process(z["pcm"][None], T, hop)["db"][0, :, 0]
+    truth = fp64_truth_db(z["pcm"][0], z["window"], float(z["window_sum"]), T, hop, g=np.float64(np.float32(0.65)))
+    lin = lambda d: np.power(10.0, np.asarray(d, np.float64) / 20.0)
+    peak = lin(truth).max(axis=-1, keepdims=True)
+    err_gpu = (np.abs(lin(got) - lin(truth)) / peak).max()
+    err_ref = (np.abs(lin(z["db"][:, 0]) - lin(truth)) / peak).max()
+    assert err_ref < 1e-6 and err_gpu < 1e-6, (err_gpu, err_ref)
+    assert err_gpu < 4 * err_ref + 2e-7, (err_gpu, err_ref)
+    # and in dB on the bins that matter (within 60 dB of the frame peak)
+    strong = lin(truth) >= peak * 1e-3
+    assert np.abs(got - truth)[strong].max() < 1e-3

@@ -89,3 +89,54 @@ def test_r2c_against_float64_dft():
         x = rng.standard_normal(n).astype(np.float32)
         t = np.fft.rfft(x.astype(np.float64))
         assert np.abs(r2c(x) - t).max() / np.abs(t).max() < 5e-7
+
+
+STALL = sorted((Path(__file__).parent / "golden").glob("stall_*.npz"))
+
+
+def stall_calls(z):
+    """Engine-call view of a stall fixture: [(pcm_view [cc, samples], n_frames, skip[n_frames])]."""
+    hop, N = int(z["hop"]), json.loads(str(z["settings"]))["fft_size"]
+    out = []
+    for c in json.loads(str(z["calls"])):
+        n = int(c["n_frames"])
+        out.append((z["pcm"][:, c["offset"]: c["offset"] + (n - 1) * hop + N], n, np.array(c["skip"], np.uint8)))
+    return out
+
+
+@pytest.mark.parametrize("path", STALL, ids=[p.stem for p in STALL])
+def test_oracle_reproduces_reference_not_enough_audio(path):
+    """'Not enough audio' ticks (src/source_generic.cpp:55-61) as the compiled reference produced them when audio was
+    stamped ahead of the tick clock; the oracle is driven with frame = NULL on the skipped ticks."""
+    z, settings = _load(path)
+    o = OracleSource(settings, channels=int(z["channels"]))
+    hop, N = int(z["hop"]), settings["fft_size"]
+    t = 0
+    assert sum(int(s.sum()) for _, _, s in stall_calls(z)) >= 2, "fixture must contain skipped ticks"
+    for pcm, n, skip in stall_calls(z):
+        for i in range(n):
+            frames = [None if skip[i] else pcm[ch, i * hop: i * hop + N] for ch in range(pcm.shape[0])]
+            o.tick(frames, float(z["seconds"]))
+            got = np.stack([o.decibels(ch) for ch in range(o.display_channels)])
+            rep = parity_report(got, z["db"][t], db_min=float(z["db_min"]))
+            assert rep["ok"], (t, rep)
+            assert o.last_silent == bool(z["silent"][t]), t
+            t += 1
+    assert t == int(z["n_frames"])
+
+
+def test_fp64_arbiter_reference_and_oracle():
+    """the error of the reference's FFTW path (golden vectors) and of the oracle's own fp32 FFT against
+    a double-precision ground truth computed from the same float32 window table.  Both are ~1e-7 normwise; the GPU
+    variant of this test (tests/test_gpu_scale.py) holds the CUDA path to the same yardstick."""
+    from helpers import fp64_truth_db
+
+    z, settings = _load(Path(__file__).parent / "golden" / "case_c3_mono_2048_hann.npz")
+    T, hop = int(z["n_frames"]), int(z["hop"])
+    truth = fp64_truth_db(z["pcm"][0], z["window"], float(z["window_sum"]), T, hop, g=np.float64(np.float32(0.65)))
+    got = OracleSource(settings, channels=1).run_stft(z["pcm"], T, hop)["db"][:, 0]
+    lin = lambda d: np.power(10.0, np.asarray(d, np.float64) / 20.0)
+    peak = lin(truth).max(axis=-1, keepdims=True)
+    err_ref = (np.abs(lin(z["db"][:, 0]) - lin(truth)) / peak).max()
+    err_port = (np.abs(lin(got) - lin(truth)) / peak).max()
+    assert err_ref < 1e-6 and err_port < 1e-6, (err_ref, err_port)

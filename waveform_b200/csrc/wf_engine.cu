@@ -38,6 +38,9 @@ struct wf_engine {
     bool ev_valid = false;
     std::string last_error;
     int64_t launches = 0;
+    std::string last_kernel;    // name of the spectrum kernel the most recent launch_range dispatched to (wf_last_kernel_name)
+    bool hold_implicit = false; // some stream may carry flags bit 3 (m_decibels mirror left implicit by the N=2048 kernel)
+    bool lazy_hold = true;      // WF_LAZY_HOLD=0: always write the mirror (A/B tests)
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
@@ -196,8 +199,8 @@ int launch_fused(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra_
 {
     using G = Geo<N>;
     const size_t smem = (size_t)G::GROUPS * G::BUF * sizeof(float2) + extra_smem;
-    static thread_local size_t configured[8] = {0};
-    int dev = e->device & 7;
+    static thread_local size_t configured[64] = {0};
+    int dev = e->device & 63;
     if(smem > 48 * 1024 && configured[dev] < smem)
     {
         WF_CUDA(e, cudaFuncSetAttribute(stft_fused_kernel<N, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -207,6 +210,7 @@ int launch_fused(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra_
     stft_fused_kernel<N, CC><<<grid, G::CTA, smem, st>>>(kp);
     WF_CUDA(e, cudaGetLastError());
     e->launches++;
+    e->last_kernel = "stft_fused_kernel<" + std::to_string(N) + "," + std::to_string(CC) + ">";
     return WF_OK;
 }
 
@@ -249,8 +253,11 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         {
             const bool feat = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask;
             const int x = feat ? 3 : (kp.out_peak ? 1 : 0);
-            WF_CUDA(e, v3_launch(e->tab.N, CC, pick_v3_r(e, kp), x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, display, e->device));
+            const int r = pick_v3_r(e, kp);
+            WF_CUDA(e, v3_launch(e->tab.N, CC, r, x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, display, e->device));
             e->launches++;
+            e->last_kernel = "stft_v3_kernel<" + std::to_string(e->tab.N) + "," + std::to_string(CC) + "," + std::to_string(r) +
+                             "," + std::to_string(x) + ">";
             return WF_OK;
         }
         const int R = pick_wide_r(e, kp, display);
@@ -258,6 +265,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         {
             WF_CUDA(e, wide_launch(e->tab.N, CC, R, kp, st, display, e->device));
             e->launches++;
+            e->last_kernel = "stft_wide_kernel<" + std::to_string(e->tab.N) + "," + std::to_string(CC) + "," + std::to_string(R) + ">";
             return WF_OK;
         }
     }
@@ -289,8 +297,8 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
             return rc;
         plan.scratch = reinterpret_cast<float2 *>(e->s_scratch);
     }
-    static thread_local size_t configured[8] = {0};
-    const int dev = e->device & 7;
+    static thread_local size_t configured[64] = {0};
+    const int dev = e->device & 63;
     if(smem > 48 * 1024 && configured[dev] < smem)
     {
         WF_CUDA(e, cudaFuncSetAttribute(stft_anyn_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -299,6 +307,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
     stft_anyn_kernel<CC><<<grid, kAnyThreads, smem, st>>>(kp, plan);
     WF_CUDA(e, cudaGetLastError());
     e->launches++;
+    e->last_kernel = "stft_anyn_kernel<" + std::to_string(CC) + "> N=" + std::to_string(e->tab.N);
     return WF_OK;
 }
 
@@ -314,8 +323,8 @@ static void fast2048_geometry(int n_streams, int sm_count, int max_wpc, int *war
 template<int MAXW, bool TSM, bool GATE, bool EXTRA>
 int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
 {
-    static thread_local bool configured[8] = {false};
-    const int dev = e->device & 7;
+    static thread_local bool configured[64] = {false};
+    const int dev = e->device & 63;
     if(!configured[dev])
     {
         WF_CUDA(e, cudaFuncSetAttribute(stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA>,
@@ -341,6 +350,8 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
     cfg.numAttrs = 1;
     WF_CUDA(e, cudaLaunchKernelEx(&cfg, stft2048_fast_kernel<MAXW, TSM, GATE, EXTRA>, kp));
     e->launches++;
+    e->last_kernel = "stft2048_fast_kernel<" + std::to_string(MAXW) + "," + std::to_string((int)TSM) + "," + std::to_string((int)GATE) +
+                     "," + std::to_string((int)EXTRA) + "> grid " + std::to_string(grid) + " x " + std::to_string(wpc) + " warps";
     return WF_OK;
 }
 
@@ -348,8 +359,8 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
 template<bool TSM, bool GATE, bool EXTRA>
 int launch_pair2048(wf_engine *e, const KParams &kp, cudaStream_t st)
 {
-    static thread_local bool configured[8] = {false};
-    const int dev = e->device & 7;
+    static thread_local bool configured[64] = {false};
+    const int dev = e->device & 63;
     if(!configured[dev])
     {
         WF_CUDA(e, cudaFuncSetAttribute(stft2048_pair_kernel<TSM, GATE, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -430,32 +441,34 @@ int fill_device(wf_engine *e, float *p, long long n, float v, cudaStream_t st)
     return WF_OK;
 }
 
-int init_state(wf_engine *e, int first, int count, bool reset_semantics, cudaStream_t st)
+// Write out every implicit m_decibels mirror (see materialize_hold_kernel) before something other than the N=2048
+// warp-per-stream kernel looks at hold_db.
+int materialize_hold(wf_engine *e, cudaStream_t st)
+{
+    if(!e->hold_implicit)
+        return WF_OK;
+    const Tables &t = e->tab;
+    const int S = t.cfg.max_streams;
+    materialize_hold_kernel<<<std::min(S, e->sm_count * 8), 256, 0, st>>>(e->d_state, e->d_hold, e->d_flags, S, t.B,
+                                                                          t.output_channels, t.db_min);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
+    e->hold_implicit = false;
+    return WF_OK;
+}
+
+// Fresh streams (wf_create): m_tsmooth_buf = 0, m_decibels = DB_MIN, m_last_silent = false (src/source.cpp:1176-1180, 1236).
+int init_state(wf_engine *e, int first, int count, cudaStream_t st)
 {
     const Tables &t = e->tab;
     const int cc = t.cfg.capture_channels, och = t.output_channels, B = t.B;
     WF_CUDA(e, cudaMemsetAsync(e->d_state + (size_t)first * cc * B, 0, (size_t)count * cc * B * sizeof(float), st));
-    if(reset_semantics && och > t.display_channels)
-    {
-        // the timeout branch only refills the DISPLAY channels with DB_MIN (src/source_generic.cpp:43-45);
-        // slot 1 of a 2ch->mono mix keeps its last linear magnitudes.
-        for(int s = first; s < first + count; ++s)
-        {
-            int rc = fill_device(e, e->d_hold + (size_t)s * och * B, (long long)t.display_channels * B, t.db_min, st);
-            if(rc)
-                return rc;
-        }
-    }
-    else
-    {
-        int rc = fill_device(e, e->d_hold + (size_t)first * och * B, (long long)count * och * B, t.db_min, st);
-        if(rc)
-            return rc;
-    }
+    int rc = fill_device(e, e->d_hold + (size_t)first * och * B, (long long)count * och * B, t.db_min, st);
+    if(rc)
+        return rc;
     // flags: bit0 last_silent; bit1/2: previous outputs all <= floor-10 (DB_MIN is)
     const bool below = !(t.db_min > (float)(t.cfg.floor_db - 10));
-    const unsigned char fl = (unsigned char)((reset_semantics ? 1u : 0u) | (below ? 6u : 0u));
-    WF_CUDA(e, cudaMemsetAsync(e->d_flags + first, fl, (size_t)count, st));
+    WF_CUDA(e, cudaMemsetAsync(e->d_flags + first, below ? 6 : 0, (size_t)count, st));
     return WF_OK;
 }
 
@@ -585,6 +598,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->fast_min_streams = atoi(fms);
         const char *v3 = getenv("WF_V3");
         e->use_v3 = !(v3 && v3[0] == '0');
+        const char *lh = getenv("WF_LAZY_HOLD");
+        e->lazy_hold = !(lh && lh[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
         if(wo)
             e->fast_wpc_override = atoi(wo);
@@ -641,7 +656,7 @@ int wf_create(const wf_config *cfg, wf_engine **out)
     WF_CUDA_C(cudaMalloc((void **)&e->d_state, S * t.cfg.capture_channels * t.B * sizeof(float)));
     WF_CUDA_C(cudaMalloc((void **)&e->d_hold, S * t.output_channels * t.B * sizeof(float)));
     WF_CUDA_C(cudaMalloc((void **)&e->d_flags, S));
-    WF_TRY(init_state(e, 0, (int)S, false, e->stream));
+    WF_TRY(init_state(e, 0, (int)S, e->stream));
     WF_CUDA_C(cudaStreamSynchronize(e->stream));
 #undef WF_TRY
 #undef WF_CUDA_C
@@ -864,7 +879,15 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+        kp.lazy_hold = e->lazy_hold ? 1 : 0;
+        if(kp.lazy_hold)
+            e->hold_implicit = true;
         return dispatch_fast2048(e, kp, st, x);
+    }
+    {
+        const int rc = materialize_hold(e, st); // the other kernels read hold_db as it is
+        if(rc)
+            return rc;
     }
     return (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
 }
@@ -1072,9 +1095,17 @@ int wf_reset_state(wf_engine *e, int32_t first, int32_t count)
     if(count == 0)
         return WF_OK;
     WF_CUDA(e, cudaSetDevice(e->device));
-    int rc = init_state(e, first, count, true, e->stream);
-    if(rc)
-        return rc;
+    // on the device, per stream, so that a stream that is already silent keeps its buffers exactly as the reference's
+    // early return does (src/source_generic.cpp:38-39)
+    const Tables &t = e->tab;
+    const bool below = !(t.db_min > (float)(t.cfg.floor_db - 10));
+    const unsigned char fl = (unsigned char)(1u | (below ? 6u : 0u));
+    const size_t B = (size_t)t.B;
+    spectrum_reset_kernel<<<std::min(count, e->sm_count * 8), 256, 0, e->stream>>>(
+        e->d_state + (size_t)first * t.cfg.capture_channels * B, e->d_hold + (size_t)first * t.output_channels * B, e->d_flags + first,
+        count, (int)(t.cfg.capture_channels * B), (int)(t.output_channels * B), (int)(t.display_channels * B), t.db_min, fl);
+    WF_CUDA(e, cudaGetLastError());
+    e->launches++;
     WF_CUDA(e, cudaStreamSynchronize(e->stream));
     return WF_OK;
 }
@@ -1087,6 +1118,11 @@ int wf_get_state(wf_engine *e, int32_t first, int32_t count, float *tsmooth, flo
     if(first < 0 || count < 0 || (int64_t)first + count > t.cfg.max_streams)
         return set_err(e, WF_ERR_CAPACITY, "state range out of bounds");
     WF_CUDA(e, cudaSetDevice(e->device));
+    {
+        const int rc = materialize_hold(e, e->stream);
+        if(rc)
+            return rc;
+    }
     WF_CUDA(e, cudaStreamSynchronize(e->stream));
     const size_t cc = (size_t)t.cfg.capture_channels, och = (size_t)t.output_channels, B = (size_t)t.B;
     if(tsmooth)
@@ -1111,6 +1147,11 @@ int wf_set_state(wf_engine *e, int32_t first, int32_t count, const float *tsmoot
     if(first < 0 || count < 0 || (int64_t)first + count > t.cfg.max_streams)
         return set_err(e, WF_ERR_CAPACITY, "state range out of bounds");
     WF_CUDA(e, cudaSetDevice(e->device));
+    {
+        const int rc = materialize_hold(e, e->stream);
+        if(rc)
+            return rc;
+    }
     WF_CUDA(e, cudaStreamSynchronize(e->stream));
     const size_t cc = (size_t)t.cfg.capture_channels, och = (size_t)t.output_channels, B = (size_t)t.B;
     if(tsmooth)
@@ -1201,6 +1242,8 @@ int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_fr
 }
 
 int64_t wf_launch_count(const wf_engine *e) { return e ? e->launches : 0; }
+
+const char *wf_last_kernel_name(const wf_engine *e) { return e ? e->last_kernel.c_str() : ""; }
 
 float wf_last_kernel_ms(wf_engine *e)
 {

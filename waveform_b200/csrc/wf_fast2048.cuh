@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         const unsigned char fl = p.flags[s];
         bool last_silent = (fl & 1u) != 0;
         bool prev_out_silent = (fl & 2u) != 0;
+        // bit 3: the m_decibels mirror of this stream was NOT written by the previous call because it equals
+        // dbfs(state) (see the end of this loop); it is rebuilt from the state wherever it is needed
+        const bool hold_lazy = (fl & 8u) != 0;
         bool last_from_state = false; // the last tick's outputs are dbfs(state) (normal tick), not a hold / quirk
         const float *pcm_s = p.pcm + (size_t)s * p.stream_stride;
         float *hold_s = p.hold_db + (size_t)s * B;
@@ -217,6 +220,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                     for(int n1 = 0; n1 < 32; ++n1)
                         v[n1] = buf64[n1 * 33 + lane];
                     __syncwarp(); // all generic-proxy accesses to buf are done: it can take the next frame
+                    // the next stream's EMA state (4 KB, one 128-byte line per lane) is pulled into L2 now, so that the
+                    // synchronous state load at the top of the stream loop does not pay DRAM latency (matters when a
+                    // stream has few frames: the 65536 x 1 layout loads a state per frame)
+                    if(t + 1 == T && li + warps_per_cta < n_local)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (size_t)(s + warps_per_cta * G) * B + lane * 32));
                     // prefetch the next frame (or the next stream's first frame) under pass B + epilogue
                     if(lane == 0)
                     {
@@ -340,26 +348,52 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             {
                 // ---- rare path: tick returned early (hold, src/source_generic.cpp:138-139) or the channel was
                 //      skipped while the tick went on (stale dB re-converted) ----
+                // Previous outputs: the row of tick t-1, or (t == 0) the engine's m_decibels mirror — which the previous
+                // call may have left implicit (hold_lazy: it is dbfs(state), and the state is in shared memory).
                 const float *prev_db = (t > 0) ? (odb - B) : hold_s;
+                const bool from_state = (t == 0) && hold_lazy;
 #pragma unroll 1
-                for(int k = lane; k < B; k += 32)
+                for(int q = 0; q < 16; ++q)
                 {
-                    float o = prev_db[k];
+                    const int k1 = lane + 32 * q;
+                    const int k2 = (q == 0) ? k2_q0 : (kb + 32 * (31 - q));
+                    float o1, o2;
+                    if(from_state)
+                    {
+                        const float2 stv = sst[q * 32];
+                        pk::split(dbfs2(stv.x, stv.y, p.db_min), o1, o2);
+                    }
+                    else
+                    {
+                        o1 = prev_db[k1];
+                        o2 = prev_db[k2];
+                    }
                     if(!last_silent)
                     {
-                        o = dbfs(o, p.db_min);
-                        if(EXTRA && k >= 1)
+                        o1 = dbfs(o1, p.db_min);
+                        o2 = dbfs(o2, p.db_min);
+                        if(EXTRA)
                         {
                             if(p.normalize)
-                                o += vc;
+                            {
+                                if(k1 >= 1)
+                                    o1 += vc;
+                                o2 += vc;
+                            }
                             if(p.rolloff != nullptr)
-                                o = fmaxf(o - __ldg(p.rolloff + k), p.db_min);
+                            {
+                                if(k1 >= 1)
+                                    o1 = fmaxf(o1 - __ldg(p.rolloff + k1), p.db_min);
+                                o2 = fmaxf(o2 - __ldg(p.rolloff + k2), p.db_min);
+                            }
                         }
                     }
-                    outs &= !(o > p.floor_m10);
-                    if(k >= 1)
-                        peak = fmaxf(peak, o);
-                    odb[k] = o;
+                    outs &= !(o1 > p.floor_m10) & !(o2 > p.floor_m10);
+                    if(k1 >= 1)
+                        peak = fmaxf(peak, o1);
+                    peak = fmaxf(peak, o2);
+                    odb[k1] = o1;
+                    odb[k2] = o2;
                 }
                 last_from_state = false;
             }
@@ -383,6 +417,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             float *sp = p.state + (size_t)s * B;
             const float *last = p.out_db + ((size_t)s * T + (T - 1)) * B;
             const bool plain = !EXTRA || (!p.normalize && p.rolloff == nullptr);
+            // The mirror equals dbfs(state) after a normal tick without volume / roll-off post-processing: do not spend
+            // 4 KB of HBM writes per stream on it, set bit 3 instead (the engine materialises it on demand, see
+            // materialize_hold_kernel; this kernel rebuilds it from the state in its rare path).
+            const bool lazy = last_from_state && plain && (p.lazy_hold != 0);
 #pragma unroll
             for(int q = 0; q < 16; ++q)
             {
@@ -391,7 +429,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                 const float2 stv = sst[q * 32];
                 sp[k1] = stv.x;
                 sp[k2] = stv.y;
-                if(p.write_hold)
+                if(p.write_hold && !lazy)
                 {
                     if(last_from_state && plain)
                     {
@@ -408,7 +446,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                 }
             }
             if(lane == 0)
-                p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent ? 2u : 0u) | 4u);
+                p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent ? 2u : 0u) | 4u | (lazy ? 8u : 0u));
         }
         __syncwarp();
     }

@@ -57,6 +57,7 @@ struct KParams {
     int normalize;
     float vol_target, max_gain;
     int write_hold;   // write final m_decibels mirror to hold_db at the end of the call
+    int lazy_hold;    // N=2048 warp-per-stream kernel: leave the mirror implicit (flags bit 3) when it equals dbfs(state)
     // interpolation
     const float *interp_idx;
     const float *interp_w;
@@ -862,6 +863,49 @@ __global__ void __launch_bounds__(Geo<N>::CTA, Geo<N>::MINB) stft_fused_kernel(c
         }
         if(tid == 0)
             p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent0 ? 2u : 0u) | (prev_out_silent1 ? 4u : 0u));
+    }
+}
+
+// Streams whose m_decibels mirror was left implicit by stft2048_fast_kernel (flags bit 3: mirror == dbfs(state), one
+// capture channel, one display channel) get it written out here, with the same MUFU.LG2 arithmetic the kernel used for
+// the outputs.  Run by the engine before anything else reads hold_db (other kernels, wf_get_state / wf_set_state).
+static __global__ void materialize_hold_kernel(const float *state, float *hold_db, unsigned char *flags, int n_streams, int B,
+                                               int och, float db_min)
+{
+    for(int s = blockIdx.x; s < n_streams; s += gridDim.x)
+    {
+        const unsigned char fl = flags[s];
+        if(!(fl & 8u))
+            continue;
+        for(int k = threadIdx.x; k < B; k += blockDim.x)
+        {
+            float l;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(state[(size_t)s * B + k]));
+            hold_db[(size_t)s * och * B + k] = fmaxf(l * 6.02059991327962390f, db_min);
+        }
+        __syncthreads();
+        if(threadIdx.x == 0)
+            flags[s] = (unsigned char)(fl & ~8u);
+    }
+}
+
+// Timeout / hidden branch of tick_spectrum (src/source_generic.cpp:36-48) for streams [0, n_streams): a stream that is
+// already m_last_silent returns early there and keeps its buffers; the others get m_tsmooth_buf := 0, the DISPLAY rows of
+// m_decibels := DB_MIN (slot 1 of a 2ch->mono mix keeps its last linear magnitudes, :43-45) and m_last_silent := true.
+static __global__ void spectrum_reset_kernel(float *state, float *hold_db, unsigned char *flags, int n_streams, int ccB, int ochB,
+                                             int dchB, float db_min, unsigned char new_flags)
+{
+    for(int s = blockIdx.x; s < n_streams; s += gridDim.x)
+    {
+        if(flags[s] & 1u)
+            continue;
+        for(int i = threadIdx.x; i < ccB; i += blockDim.x)
+            state[(size_t)s * ccB + i] = 0.0f;
+        for(int i = threadIdx.x; i < dchB; i += blockDim.x)
+            hold_db[(size_t)s * ochB + i] = db_min;
+        __syncthreads();
+        if(threadIdx.x == 0)
+            flags[s] = new_flags;
     }
 }
 

@@ -12,8 +12,8 @@ template<int N, int CC, int R, int EXTRA>
 cudaError_t launch_one(const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, bool display, int device)
 {
     const size_t smem = v3::smem_bytes<N>(kp.dch, kp.scratch_q, display, CC, R);
-    static thread_local size_t configured[8] = {0};
-    const int dev = device & 7;
+    static thread_local size_t configured[64] = {0};
+    const int dev = device & 63;
     if(smem > 48 * 1024 && configured[dev] < smem)
     {
         cudaError_t err = cudaFuncSetAttribute(stft_v3_kernel<N, CC, R, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -391,6 +391,8 @@ int wf_wave_create(const wf_wave_config *cfg, wf_wave **out)
         return bail(werr(w, WF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major,
                          prop.minor));
     w->sm_count = prop.multiProcessorCount;
+    if(2 * (size_t)cfg->width * sizeof(float) > 48 * 1024) // widths above 6144: both scrolling rings exceed the default 48 KB
+        WFW_C(cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (size_t)cfg->width * sizeof(float))));
     WFW_C(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     WFW_C(cudaEventCreate(&w->ev0));
     WFW_C(cudaEventCreate(&w->ev1));

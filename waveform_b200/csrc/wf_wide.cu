@@ -13,8 +13,8 @@ template<int N, int CC, int R>
 cudaError_t launch_one(const KParams &kp, cudaStream_t st, bool display, int device)
 {
     const size_t smem = wide::smem_bytes<N>(kp.dch, kp.scratch_q, display);
-    static thread_local size_t configured[8] = {0};
-    const int dev = device & 7;
+    static thread_local size_t configured[64] = {0};
+    const int dev = device & 63;
     if(smem > 48 * 1024 && configured[dev] < smem)
     {
         cudaError_t err =

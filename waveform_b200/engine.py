@@ -42,7 +42,8 @@ TABLE_WINDOW, TABLE_SLOPE, TABLE_ROLLOFF, TABLE_INTERP_INDICES, TABLE_INTERP_WEI
 EXPORTS = [
     "wf_abi_version", "wf_strerror", "wf_last_error", "wf_config_init", "wf_create", "wf_destroy", "wf_get_info",
     "wf_get_table", "wf_gravity", "wf_process", "wf_process_async", "wf_synchronize", "wf_reset_state",
-    "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_preview_table",
+    "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_last_kernel_name",
+    "wf_preview_table",
     "wf_meter_config_init", "wf_meter_create", "wf_meter_destroy", "wf_meter_last_error", "wf_meter_window",
     "wf_meter_process", "wf_meter_process_async", "wf_meter_reset", "wf_meter_launch_count", "wf_meter_last_kernel_ms",
     "wf_wave_config_init", "wf_wave_create", "wf_wave_destroy", "wf_wave_last_error", "wf_wave_process",
@@ -169,6 +170,8 @@ def load_library():
     L.wf_launch_count.argtypes = [vp]
     L.wf_last_kernel_ms.restype = C.c_float
     L.wf_last_kernel_ms.argtypes = [vp]
+    L.wf_last_kernel_name.restype = C.c_char_p
+    L.wf_last_kernel_name.argtypes = [vp]
     L.wf_meter_config_init.argtypes = [C.POINTER(WfMeterConfig)]
     L.wf_meter_create.argtypes = [C.POINTER(WfMeterConfig), C.POINTER(vp)]
     L.wf_meter_destroy.argtypes = [vp]
@@ -357,6 +360,9 @@ class Engine:
     def last_kernel_ms(self) -> float:
         return float(self.L.wf_last_kernel_ms(self.h))
 
+    def last_kernel_name(self) -> str:
+        return self.L.wf_last_kernel_name(self.h).decode()
+
     # ---- processing ----
     def process_raw(self, pcm_ptr, n_streams, n_frames, hop, stream_stride, channel_stride, *, first_stream=0,
                     seconds=1.0 / 60.0, input_rms=None, skip_mask=None, out_db=None, out_points=None,
@@ -421,10 +427,18 @@ class Engine:
         if want_pixels:
             out["pixels"] = mk((S, n_frames, dch, P), f32)
             out["min"] = mk((S, n_frames, 2), f32)
+        # CUDA tensors: launch on torch's CURRENT stream, so the kernel is ordered after whatever produced `pcm` and before
+        # whatever consumes the outputs (torch semantics: asynchronous, stream-ordered).  Host arrays: the engine's own
+        # stream, synchronised before returning.
+        stream = None
+        if is_torch:
+            import torch
+            stream = torch.cuda.current_stream(pcm.device).cuda_stream
         self.process_raw(_ptr(pcm), S, n_frames, hop, cc * ns, ns, first_stream=first_stream, seconds=seconds,
                          input_rms=_ptr(input_rms), skip_mask=_ptr(skip_mask), out_db=_ptr(out.get("db")),
                          out_points=_ptr(out.get("points")), out_silent=_ptr(out.get("silent")),
-                         out_peak=_ptr(out.get("peak")), out_pixels=_ptr(out.get("pixels")), out_min=_ptr(out.get("min")))
+                         out_peak=_ptr(out.get("peak")), out_pixels=_ptr(out.get("pixels")), out_min=_ptr(out.get("min")),
+                         stream=stream, sync=not is_torch)
         return out
 
     def synchronize(self):
@@ -450,9 +464,15 @@ class Engine:
         self._check(self.L.wf_set_state(self.h, first_stream, count, _ptr(ts), _ptr(hold), _ptr(flags)))
 
     def peak_normalize(self, data, peak, target_db: float, max_gain: float, stream=None):
-        """In-place: data[s, t, ch, k>=1] += min(target_db - peak[t], max_gain)."""
+        """In-place: data[s, t, ch, k>=1] += min(target_db - peak[t], max_gain).  CUDA tensors run on torch's current
+        stream unless `stream` is given (so a preceding all_reduce on that stream is ordered before the pass)."""
         S, T, dch, row = data.shape
         assert dch == self.display_channels
+        if stream is None and hasattr(data, "data_ptr") and getattr(data, "is_cuda", False):
+            import torch
+            stream = torch.cuda.current_stream(data.device).cuda_stream
+        if stream == 0:
+            stream = 1  # cudaStreamLegacy; NULL would select the engine's private stream
         self._check(self.L.wf_peak_normalize(self.h, _ptr(data), S, T, row, _ptr(peak), target_db, max_gain, stream))
 
 
