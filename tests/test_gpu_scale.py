@@ -68,7 +68,7 @@ def _run_and_check(settings, channels, S, T, hop_div=1, zero_every=7, want_point
         out = {k: torch.cat([p[k] for p in parts], dim=1) for k in parts[0]}
     torch.cuda.synchronize()
     pick = _sample_streams(S, n_random=n_random)
-    assert len(pick) >= min(S, 48)
+    assert len(pick) >= min(S, 36)
     idx = torch.tensor(pick, device="cuda")
     got_db = out["db"][idx].cpu().numpy()
     got_sil = out["silent"][idx].cpu().numpy()
@@ -85,7 +85,8 @@ def _run_and_check(settings, channels, S, T, hop_div=1, zero_every=7, want_point
     db = out["db"]
     assert bool(torch.isfinite(db).all()) and float(db.min()) >= eng.db_min - 1e-3
     row_max = db.amax(dim=(1, 2, 3))
-    assert float(row_max.min()) > -200.0, "a stream's outputs were never written"
+    audible = pcm[:, :, : ns].abs().amax(dim=(1, 2)) > 0          # a stream of pure digital silence stays at DB_MIN
+    assert float(row_max[audible].min()) > -200.0, "a stream's outputs were never written"
     return eng, out, pcm
 
 
@@ -97,17 +98,71 @@ FAST_SHAPES = [
 
 
 @pytest.mark.parametrize("S,T,calls", FAST_SHAPES)
-def test_fast2048_parity_at_measured_geometry(S, T, calls):
+def test_fast2048_parity_at_measured_geometry(S, T, calls, monkeypatch):
+    """The warp-per-stream kernel at its real launch geometries (WF_TEAM_W=1 keeps the small shapes on it too)."""
+    monkeypatch.setenv("WF_TEAM_W", "1")
     settings = {"fft_size": 2048, "window": "hann", "gravity": 0.65}
     eng, out, _ = _run_and_check(settings, 1, S, T, calls=calls)
     assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
 
 
-@pytest.mark.parametrize("S,T", [(256, 64), (512, 48), (148, 40)])
-def test_n2048_few_streams_many_ticks(S, T):
-    """Few streams x many ticks (SURVEY §8(d) C3 '256 x 256' family): whatever kernel the engine routes this to, parity holds."""
+TEAM_SHAPES = [
+    # (S, T, calls, W expected): few streams x many ticks (SURVEY §8(d) C3 '256 x 256' family) -> a team of W warps per stream
+    (256, 64, 2, 8), (512, 48, 2, 4), (148, 40, 3, 16), (1024, 21, 2, 4), (300, 9, 1, 4), (37, 5, 1, 4), (600, 7, 2, 4), (1184, 6, 1, 4),
+]
+
+
+@pytest.mark.parametrize("S,T,calls,W", TEAM_SHAPES)
+def test_team2048_parity_and_bit_identity(S, T, calls, W, monkeypatch):
+    """wf_team2048.cuh under the engine's own routing: parity against the oracle on the sampled streams, and bit-identical
+    outputs / state to the warp-per-stream kernel on EVERY stream (the recurrences are only distributed over bins)."""
+    import torch
+    from waveform_b200 import Engine
+
     settings = {"fft_size": 2048, "window": "hann", "gravity": 0.65}
-    _run_and_check(settings, 1, S, T, calls=2)
+    eng, out, pcm = _run_and_check(settings, 1, S, T, calls=calls)
+    assert eng.last_kernel_name().startswith(f"stft2048_team_kernel<{W},"), eng.last_kernel_name()
+    monkeypatch.setenv("WF_TEAM_W", "1")
+    ref_eng = Engine(settings, channels=1, max_streams=S)
+    ref = ref_eng.process(pcm, T, 2048)
+    torch.cuda.synchronize()
+    assert ref_eng.last_kernel_name().startswith("stft2048_fast")
+    assert torch.equal(out["db"], ref["db"]) and torch.equal(out["silent"], ref["silent"])
+    a, b = eng.get_state(), ref_eng.get_state()
+    for key in ("tsmooth", "hold_db", "flags"):
+        assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("W", [4, 8, 16])
+def test_team2048_all_options_match_fast_kernel(W, monkeypatch):
+    """Slope, fast peaks, roll-off, volume normalisation, skip mask and the peak output through the team kernel's EXTRA
+    variant: bit-identical to the warp-per-stream kernel, and within parity of the oracle."""
+    import torch
+    from waveform_b200 import Engine
+
+    settings = {"fft_size": 2048, "window": "hamming", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0, "fast_peaks": True,
+                "normalize_volume": True, "gravity": 0.4, "floor": -45}
+    S, T, N = 21, 35, 2048
+    pcm = synth_pcm(S, 1, T * N, zero_frames=[(1, 3, 9), (2, 0, 35), (5, 10, 12), (7, 14, 30)], frame_len=N, hop=N)
+    rng = np.random.default_rng(3)
+    rms = (0.02 + 0.3 * rng.uniform(size=(S, T))).astype(np.float32)
+    skip = (rng.uniform(size=(S, T)) < 0.1).astype(np.uint8)
+    x, r, k = torch.from_numpy(pcm).cuda(), torch.from_numpy(rms).cuda(), torch.from_numpy(skip).cuda()
+    outs = []
+    for w in (W, 1):
+        monkeypatch.setenv("WF_TEAM_W", str(w))
+        eng = Engine(settings, channels=1, max_streams=S)
+        a = eng.process(x[:, :, : 16 * N].contiguous(), 16, N, input_rms=r[:, :16].contiguous(), skip_mask=k[:, :16].contiguous(), want_peak=True)
+        b = eng.process(x[:, :, 16 * N:].contiguous(), T - 16, N, input_rms=r[:, 16:].contiguous(), skip_mask=k[:, 16:].contiguous(), want_peak=True)
+        torch.cuda.synchronize()
+        name = eng.last_kernel_name()
+        assert name.startswith(f"stft2048_team_kernel<{w},1>" if w > 1 else "stft2048_fast"), name
+        outs.append(({key: torch.cat([a[key], b[key]], dim=1 if key != "peak" else 0).cpu().numpy() for key in ("db", "silent", "peak")},
+                     eng.get_state()))
+    for key in ("db", "silent", "peak"):
+        assert np.array_equal(outs[0][0][key], outs[1][0][key]), key
+    for key in ("tsmooth", "hold_db", "flags"):
+        assert np.array_equal(outs[0][1][key], outs[1][1][key]), key
 
 
 V3_SHAPES = [
@@ -134,14 +189,16 @@ def test_other_kernels_parity_at_scale(settings, channels, S, T, hop_div, want_p
 GOLD = sorted((Path(__file__).parent / "golden").glob("case_*.npz"))
 
 
+@pytest.mark.parametrize("team_w", ["1", "0"])
 @pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
-def test_golden_vectors_spectrum_only(path):
+def test_golden_vectors_spectrum_only(path, team_w, monkeypatch):
     """The reference's golden vectors WITHOUT display outputs: for case_c3_mono_2048_hann this is the headline
     stft2048_fast_kernel (the display-points variant of this test in test_gpu_parity.py routes to the CTA-per-tick kernel)."""
     z = np.load(path, allow_pickle=False)
     settings = json.loads(str(z["settings"]))
     from waveform_b200 import Engine
 
+    monkeypatch.setenv("WF_TEAM_W", team_w)   # "1": warp-per-stream kernel; "0": the engine's routing (one stream -> a team)
     eng = Engine(settings, channels=int(z["channels"]), max_streams=1)
     rms = z["rms"][None, :] if z["rms"].size else None
     out = eng.process(z["pcm"][None], int(z["n_frames"]), int(z["hop"]), seconds=float(z["seconds"]), input_rms=rms)
@@ -149,13 +206,17 @@ def test_golden_vectors_spectrum_only(path):
     assert rep["ok"] and rep["normwise"] < 1e-6, rep
     assert np.array_equal(out["silent"][0], z["silent"])
     if path.stem == "case_c3_mono_2048_hann":
-        assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+        want = "stft2048_fast" if team_w == "1" else "stft2048_team"
+        assert eng.last_kernel_name().startswith(want), eng.last_kernel_name()
 
 
+@pytest.mark.parametrize("team_w", [1, 4, 8, 16])
 @pytest.mark.parametrize("split", [None, 7, 12])
-def test_fast2048_gate_decay_freeze_wake(split):
-    """Decay -> freeze -> wake-up on the warp-per-stream kernel (T < 32 keeps N=2048 mono on it), with the call boundary
-    inside the decay (7) and inside the frozen stretch (12): the next call must see the held dB row and both gate flags."""
+def test_fast2048_gate_decay_freeze_wake(split, team_w, monkeypatch):
+    """Decay -> freeze -> wake-up on the warp-per-stream kernel (team_w = 1) and on the team kernel (lazy team-wide gate
+    reduction), with the call boundary inside the decay (7) and inside the frozen stretch (12): the next call must see the
+    held dB row and both gate flags."""
+    monkeypatch.setenv("WF_TEAM_W", str(team_w))
     settings = {"fft_size": 2048, "window": "hann", "gravity": 0.3, "floor": -40}
     S, T, N = 5, 30, 2048
     pcm = synth_pcm(S, 1, T * N)
@@ -171,7 +232,7 @@ def test_fast2048_gate_decay_freeze_wake(split):
         a = eng.process(pcm[:, :, : split * N], split, N)
         b = eng.process(pcm[:, :, split * N:], T - split, N)
         out = {k: np.concatenate([a[k], b[k]], axis=1) for k in ("db", "silent")}
-    assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+    assert eng.last_kernel_name().startswith("stft2048_fast" if team_w == 1 else f"stft2048_team_kernel<{team_w},"), eng.last_kernel_name()
     ref_db, _, ref_sil = _oracle_rows(settings, 1, pcm, T, N)
     assert ref_sil.sum() > 10 and ref_sil[2, 21] == 0 and ref_sil[2, -1] == 1, "test must exercise freeze and wake-up"
     assert np.array_equal(out["silent"], ref_sil)

@@ -21,9 +21,7 @@
 #include "wf_anyn.cuh"
 #include "wf_wide.hpp"
 #include "wf_v3.hpp"
-#ifdef WF_BUILD_EXPERIMENTAL
-#include "experimental/wf_fast2048b.cuh"
-#endif
+#include "wf_team2048.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -46,7 +44,6 @@ struct wf_engine {
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
     bool use_pdl = true;        // WF_NO_PDL=1: launch the fast kernel without programmatic dependent launch
     int wide_r = 0;             // WF_WIDE_R=1|2|4|8: force the cluster size of the wide kernel (1 = never use it); 0 = automatic
-    char fast_kernel = 'a';     // WF_FAST_KERNEL=b selects csrc/experimental/wf_fast2048b.cuh when built with -DWF_BUILD_EXPERIMENTAL
 
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
@@ -56,6 +53,7 @@ struct wf_engine {
     // sequences (>= 32) the cluster kernel (wf_v3.cuh, up to 8 ticks of a stream in flight) is faster: measured 256x256
     // 96 -> 145 M, 512x128 185 -> 202 M, 1024x64 286 vs 242 M spectra/s (profiles/r01_layouts.txt).  WF_FAST_MIN_STREAMS overrides.
     int fast_min_streams = 768;
+    int team_w = 0;                            // WF_TEAM_W=4|8|16: force the team size of wf_team2048.cuh; 1: never use it; 0 = automatic
     bool use_v3 = true;                        // WF_V3=0: fall back to the first-generation kernels (A/B tests)
     float *d_interp_idx = nullptr, *d_interp_w = nullptr, *d_gauss = nullptr;
     int *d_band_widths = nullptr, *d_band_offsets = nullptr;
@@ -355,56 +353,10 @@ int launch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st)
     return WF_OK;
 }
 
-#ifdef WF_BUILD_EXPERIMENTAL
-template<bool TSM, bool GATE, bool EXTRA>
-int launch_pair2048(wf_engine *e, const KParams &kp, cudaStream_t st)
-{
-    static thread_local bool configured[64] = {false};
-    const int dev = e->device & 63;
-    if(!configured[dev])
-    {
-        WF_CUDA(e, cudaFuncSetAttribute(stft2048_pair_kernel<TSM, GATE, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        fastb::smem_bytes(fastb::kMaxGroups)));
-        configured[dev] = true;
-    }
-    const int grid = std::min(kp.n_streams, e->sm_count);
-    const int per_cta = (kp.n_streams + grid - 1) / grid;
-    int groups = std::max(1, std::min(fastb::kMaxGroups, per_cta));
-    if(e->fast_wpc_override > 0 && e->fast_wpc_override <= fastb::kMaxGroups)
-        groups = e->fast_wpc_override;
-    stft2048_pair_kernel<TSM, GATE, EXTRA><<<grid, groups * 64, fastb::smem_bytes(groups), st>>>(kp);
-    WF_CUDA(e, cudaGetLastError());
-    e->launches++;
-    return WF_OK;
-}
-
-int dispatch_pair2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
-{
-    const bool tsm = kp.tsmooth != 0, gate = kp.gate != 0;
-#define WF_PAIR_CASE(T, G, X)                   \
-    if(tsm == T && gate == G && extra == X)     \
-        return launch_pair2048<T, G, X>(e, kp, st);
-    WF_PAIR_CASE(true, true, false)
-    WF_PAIR_CASE(true, true, true)
-    WF_PAIR_CASE(true, false, false)
-    WF_PAIR_CASE(true, false, true)
-    WF_PAIR_CASE(false, true, false)
-    WF_PAIR_CASE(false, true, true)
-    WF_PAIR_CASE(false, false, false)
-    WF_PAIR_CASE(false, false, true)
-#undef WF_PAIR_CASE
-    return set_err(e, WF_ERR_INVALID_ARG, "pair2048 dispatch fell through");
-}
-
-#endif
 
 // Hand-specialised path for the headline shape (see wf_fast2048.cuh); everything else takes the generic kernel.
 int dispatch_fast2048(wf_engine *e, const KParams &kp, cudaStream_t st, bool extra)
 {
-#ifdef WF_BUILD_EXPERIMENTAL
-    if(e->fast_kernel == 'b')
-        return dispatch_pair2048(e, kp, st, extra);
-#endif
     const bool tsm = kp.tsmooth != 0, gate = kp.gate != 0;
     const int maxw = e->fast_maxw;
 #define WF_FAST_CASE(W, T, G, X)            \
@@ -585,9 +537,6 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *mw = getenv("WF_FAST_MAXW");
         if(mw && (atoi(mw) == 12 || atoi(mw) == 16))
             e->fast_maxw = atoi(mw);
-        const char *fk = getenv("WF_FAST_KERNEL");
-        if(fk && (fk[0] == 'a' || fk[0] == 'b'))
-            e->fast_kernel = fk[0];
         const char *np = getenv("WF_NO_PDL");
         e->use_pdl = !(np && np[0] == '1');
         const char *wr = getenv("WF_WIDE_R");
@@ -598,6 +547,9 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->fast_min_streams = atoi(fms);
         const char *v3 = getenv("WF_V3");
         e->use_v3 = !(v3 && v3[0] == '0');
+        const char *tw = getenv("WF_TEAM_W");
+        if(tw)
+            e->team_w = atoi(tw);
         const char *lh = getenv("WF_LAZY_HOLD");
         e->lazy_hold = !(lh && lh[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
@@ -874,14 +826,39 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     }
     const bool aligned16 = (((uintptr_t)kp.pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->hop & 3) == 0);
     const bool fast_ok = (N == 2048) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&
-                         !kp.out_min && aligned16 && !e->force_generic &&
-                         (kp.n_streams >= e->fast_min_streams || kp.n_frames < 32 || !e->use_v3);
+                         !kp.out_min && aligned16 && !e->force_generic;
     if(fast_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
         kp.lazy_hold = e->lazy_hold ? 1 : 0;
         if(kp.lazy_hold)
             e->hold_implicit = true;
+        // Fewer streams than 148 SMs x 16 warps: a team of W warps per stream works on W ticks at once (wf_team2048.cuh).
+        // Up to 8 streams per SM: 16 / W = 1, 2 or 4 teams per SM (a team takes its streams one after the other); measured
+        // (profiles/r02_layouts.txt) 256 x 256: 142 -> 272 M spectra/s, 512 x 128: 200 -> 310 M, 1024 x 64: 289 -> 332 M.
+        int W = 1;
+        if(e->team_w != 1)
+        {
+            const int per_sm = (kp.n_streams + e->sm_count - 1) / e->sm_count;
+            if(per_sm <= 8)
+                W = (per_sm <= 1) ? 16 : (per_sm == 2) ? 8 : 4;
+            if(e->team_w == 4 || e->team_w == 8 || e->team_w == 16)
+                W = e->team_w;
+            while(W > 1 && W > kp.n_frames)
+                W /= 2;
+            if(W == 2)
+                W = 1;
+        }
+        if(W > 1)
+        {
+            const int tpc = 16 / W;
+            const int grid = std::min(e->sm_count, kp.n_streams); // streams are dealt to SMs first, then to an SM's teams
+            WF_CUDA(e, team2048_launch(W, x, kp, grid, st, e->use_pdl, e->device));
+            e->launches++;
+            e->last_kernel = "stft2048_team_kernel<" + std::to_string(W) + "," + std::to_string((int)x) + "> grid " + std::to_string(grid) +
+                             " x " + std::to_string(tpc) + " teams";
+            return WF_OK;
+        }
         return dispatch_fast2048(e, kp, st, x);
     }
     {

@@ -13,148 +13,159 @@ namespace {
 
 constexpr float kPi = std::numbers::pi_v<float>;
 
-// log_interp, src/math_funcs.hpp:25-29
-inline float log_interp(float a, float b, float t) { return a * std::pow(b / a, t); }
+// a * (b/a)^t: geometric interpolation between a and b (≙ log_interp, src/math_funcs.hpp:25-29)
+inline float geo_lerp(float a, float b, float t) { return a * std::pow(b / a, t); }
 
-// sinc / lanczos, src/math_funcs.hpp:37-52
-inline float sinc(float x)
+// ---- FFT window ------------------------------------------------------------------------------------------------
+// Every cosine-sum window of the plugin (src/source.cpp:1190-1234) is  w[i] = a0 -+ a1 cos(1*phi) +- a2 cos(2*phi) ...
+// with phi = 2 pi i / (n-1) (symmetric form) evaluated in float32, left to right.  One generator, driven by a
+// coefficient row per window, reproduces the reference's tables bit for bit: the harmonic's angle is
+// ((2h * pi) * i) / (n-1) with the same three roundings, each term is  acc = acc (-/+) (a_h * cos(angle)).
+// (Hann is stored as 0.5 - 0.5 cos: scaling by a power of two commutes with rounding, so it equals 0.5 * (1 - cos).)
+struct CosineSum {
+    int terms;        // harmonics after a0
+    float a[4];       // a0, a1, a2, a3 (magnitudes; signs alternate -, +, -)
+};
+
+const CosineSum *cosine_sum_for(int window)
 {
-    if(x == 0.0)
-        return 1.0f;
-    const auto tmp = kPi * x;
-    return std::sin(tmp) / tmp;
+    static const CosineSum hann{1, {0.5f, 0.5f, 0.0f, 0.0f}};
+    static const CosineSum hamming{1, {0.53836f, 0.46164f, 0.0f, 0.0f}};
+    static const CosineSum blackman{2, {0.42f, 0.5f, 0.08f, 0.0f}};
+    static const CosineSum blackman_harris{3, {0.35875f, 0.48829f, 0.14128f, 0.01168f}};
+    switch(window)
+    {
+    case WF_WINDOW_HAMMING: return &hamming;
+    case WF_WINDOW_BLACKMAN: return &blackman;
+    case WF_WINDOW_BLACKMAN_HARRIS: return &blackman_harris;
+    case WF_WINDOW_POWER_OF_SINE: return nullptr;
+    default: return &hann;
+    }
 }
-inline float lanczos(float x, float w) { return (std::abs(x) < w) ? sinc(x) * sinc(x / w) : 0.0f; }
 
-// window coefficients + sequential fp32 sum, src/source.cpp:1190-1234
 void build_window(Tables &t)
 {
-    const auto &c = t.cfg;
     const size_t n = (size_t)t.N;
-    if(c.window == WF_WINDOW_NONE)
+    if(t.cfg.window == WF_WINDOW_NONE)
     {
         t.window.clear();
-        t.window_sum = (float)n;
+        t.window_sum = (float)n; // a rectangular window sums to n (src/source.cpp:1234)
         return;
     }
     t.window.resize(n);
-    const auto N = n - 1;
-    constexpr auto pi2 = 2 * kPi;
-    constexpr auto pi4 = 4 * kPi;
-    constexpr auto pi6 = 6 * kPi;
-    auto *w = t.window.data();
-    switch(c.window)
+    const size_t last = n - 1;
+    if(const CosineSum *cs = cosine_sum_for(t.cfg.window))
     {
-    case WF_WINDOW_HAMMING:
+        const float turn[3] = {2 * kPi, 4 * kPi, 6 * kPi}; // 2 pi h, h = 1..3
         for(size_t i = 0; i < n; ++i)
-            w[i] = 0.53836f - (0.46164f * std::cos((pi2 * i) / N));
-        break;
-    case WF_WINDOW_BLACKMAN:
-        for(size_t i = 0; i < n; ++i)
-            w[i] = 0.42f - (0.5f * std::cos((pi2 * i) / N)) + (0.08f * std::cos((pi4 * i) / N));
-        break;
-    case WF_WINDOW_BLACKMAN_HARRIS:
-        for(size_t i = 0; i < n; ++i)
-            w[i] = 0.35875f - (0.48829f * std::cos((pi2 * i) / N)) + (0.14128f * std::cos((pi4 * i) / N)) -
-                   (0.01168f * std::cos((pi6 * i) / N));
-        break;
-    case WF_WINDOW_POWER_OF_SINE:
-        for(size_t i = 0; i < n; ++i)
-            w[i] = std::pow(std::sin((kPi * i) / N), (float)c.sine_exponent);
-        break;
-    case WF_WINDOW_HANN:
-    default:
-        for(size_t i = 0; i < n; ++i)
-            w[i] = 0.5f * (1 - std::cos((pi2 * i) / N));
-        break;
+        {
+            float acc = cs->a[0];
+            for(int h = 0; h < cs->terms; ++h)
+            {
+                const float term = cs->a[h + 1] * std::cos((turn[h] * i) / last);
+                acc = (h & 1) ? acc + term : acc - term;
+            }
+            t.window[i] = acc;
+        }
     }
-    auto sum = 0.0f;
-    for(size_t i = 0; i < n; ++i)
-        sum += w[i];
-    t.window_sum = sum;
+    else
+    {
+        const float exponent = (float)t.cfg.sine_exponent;
+        for(size_t i = 0; i < n; ++i)
+            t.window[i] = std::pow(std::sin((kPi * i) / last), exponent);
+    }
+    // m_window_sum: one float accumulator, index order (src/source.cpp:1228-1231) — the magnitude normalisation 2/sum
+    // must see exactly the reference's rounding
+    float total = 0.0f;
+    for(float w : t.window)
+        total += w;
+    t.window_sum = total;
 }
 
-// slope modifiers, src/source.cpp:1282-1290
+// ---- slope: +3 dB-ish per decade tilt, m[i] = log10(10 * 1000^(i*slope/(B-1))) (src/source.cpp:1282-1290) ----------
 void build_slope(Tables &t)
 {
     t.slope.clear();
     if(!(t.cfg.slope > 0.0f))
         return;
-    const auto num_mods = (size_t)t.B;
-    const auto maxmod = (float)(num_mods - 1);
-    t.slope.resize(num_mods);
-    for(size_t i = 0; i < num_mods; ++i)
-        t.slope[i] = std::log10(log_interp(10.0f, 10000.0f, ((float)i * t.cfg.slope) / maxmod));
+    const size_t bins = (size_t)t.B;
+    const float top = (float)(bins - 1);
+    t.slope.resize(bins);
+    for(size_t k = 0; k < bins; ++k)
+        t.slope[k] = std::log10(geo_lerp(10.0f, 10000.0f, ((float)k * t.cfg.slope) / top));
 }
 
-// roll-off, init_rolloff src/source.cpp:898-918
+// ---- roll-off: rate dB per octave outside [cutoff_low * 2^q, cutoff_high / 2^q] (init_rolloff, src/source.cpp:898-918) ---
 void build_rolloff(Tables &t)
 {
     t.rolloff.clear();
     const auto &c = t.cfg;
     if(!((c.rolloff_q > 0.0f) && (c.rolloff_rate > 0.0f)))
         return;
-    const auto sz = (size_t)t.B;
-    const auto sr = (float)c.sample_rate;
-    const auto coeff = sr / (float)(size_t)t.N;
-    const auto ratio = std::exp2(c.rolloff_q);
-    const auto freq_low = (float)c.cutoff_low * ratio;
-    const auto freq_high = (float)c.cutoff_high / ratio;
-    t.rolloff.resize(sz);
-    t.rolloff[0] = 0.0f;
-    for(size_t i = 1u; i < sz; ++i)
+    const float hz_per_bin = (float)c.sample_rate / (float)(size_t)t.N;
+    const float shrink = std::exp2(c.rolloff_q);
+    const float knee_lo = (float)c.cutoff_low * shrink;
+    const float knee_hi = (float)c.cutoff_high / shrink;
+    // attenuation for a frequency that lies `r` times beyond a knee (r <= 1: inside the pass band)
+    auto beyond = [&](float r) { return (r > 1.0f) ? (c.rolloff_rate * std::log2(r)) : 0.0f; };
+    t.rolloff.assign((size_t)t.B, 0.0f); // bin 0 is never attenuated
+    for(size_t k = 1; k < (size_t)t.B; ++k)
     {
-        auto freq = i * coeff;
-        auto ratio_low = freq_low / freq;
-        auto ratio_high = freq / freq_high;
-        auto low_attenuation = (ratio_low > 1.0f) ? (c.rolloff_rate * std::log2(ratio_low)) : 0.0f;
-        auto high_attenuation = (ratio_high > 1.0f) ? (c.rolloff_rate * std::log2(ratio_high)) : 0.0f;
-        t.rolloff[i] = low_attenuation + high_attenuation;
+        const float hz = k * hz_per_bin;
+        t.rolloff[k] = beyond(knee_lo / hz) + beyond(hz / knee_hi);
     }
 }
 
-// make_catrom_kernel, src/filter.hpp:67-103
-void build_catrom(Tables &t, float tension)
+// ---- interpolation kernels: per display point, the taps' weights for the bins around floor(x) ---------------------
+// Catmull-Rom with tension tau (make_catrom_kernel, src/filter.hpp:67-103): tap j's weight is a cubic in the
+// fractional position u; basis[j] holds its coefficients for u^0..u^3, evaluated as a plain ascending dot product
+// starting from 0 (the rounding sequence the reference's matrix product has).
+void build_catrom(Tables &t, float tau)
 {
-    const float m[4][4] = {{0, -tension, 2 * tension, -tension},
-                           {1, 0, tension - 3, 2 - tension},
-                           {0, tension, 3 - (2 * tension), tension - 2},
-                           {0, 0, -tension, tension}};
-    const auto size = (intmax_t)t.interp_indices.size();
+    const float basis[4][4] = {{0, -tau, 2 * tau, -tau}, {1, 0, tau - 3, 2 - tau}, {0, tau, 3 - (2 * tau), tau - 2}, {0, 0, -tau, tau}};
+    const size_t points = t.interp_indices.size();
     t.interp_radius = 2;
     t.interp_taps = 4;
-    t.interp_weights.assign((size_t)size * 4, 0.0f);
-    for(intmax_t i = 0; i < size; ++i)
+    t.interp_weights.assign(points * 4, 0.0f);
+    for(size_t pt = 0; pt < points; ++pt)
     {
-        auto u = t.interp_indices[i] - std::floor(t.interp_indices[i]);
-        float row[4] = {1, u, u * u, u * u * u};
-        for(intmax_t j = 0; j < 4; ++j)
+        const float u = t.interp_indices[pt] - std::floor(t.interp_indices[pt]);
+        const float powers[4] = {1, u, u * u, u * u * u};
+        for(int tap = 0; tap < 4; ++tap)
         {
-            float sum = 0;
-            for(intmax_t k = 0; k < 4; ++k)
-                sum += row[k] * m[j][k];
-            t.interp_weights[(i * 4) + j] = sum;
+            float w = 0;
+            for(int e = 0; e < 4; ++e)
+                w += powers[e] * basis[tap][e];
+            t.interp_weights[pt * 4 + tap] = w;
         }
     }
 }
 
-// make_lanczos_kernel, src/filter.hpp:106-131
-void build_lanczos(Tables &t, intmax_t radius)
+// Lanczos window of half-width a (make_lanczos_kernel, src/filter.hpp:106-131; sinc / lanczos src/math_funcs.hpp:37-52):
+// L(d) = sinc(d) sinc(d/a) for |d| < a, taps at the 2a integer bins (int)x - a + 1 ... (int)x + a.
+void build_lanczos(Tables &t, int a)
 {
-    const auto size = (intmax_t)t.interp_indices.size();
-    t.interp_radius = (int)radius;
-    t.interp_taps = (int)(radius * 2);
-    t.interp_weights.assign((size_t)(size * radius * 2), 0.0f);
-    const auto fradius = (float)radius;
-    for(intmax_t i = 0; i < size; ++i)
+    auto sinc = [](float v) {
+        if(v == 0.0)
+            return 1.0f;
+        const auto pv = kPi * v;
+        return std::sin(pv) / pv;
+    };
+    const size_t points = t.interp_indices.size();
+    const int taps = 2 * a;
+    const float width = (float)a;
+    t.interp_radius = a;
+    t.interp_taps = taps;
+    t.interp_weights.assign(points * (size_t)taps, 0.0f);
+    for(size_t pt = 0; pt < points; ++pt)
     {
-        const auto x = t.interp_indices[i];
-        const auto ix = (intmax_t)x;
-        const auto start = ix - radius + 1;
-        const auto stop = ix + radius;
-        const auto base = i * radius * 2;
-        for(auto j = start; j <= stop; ++j)
-            t.interp_weights[base + (j - start)] = lanczos(x - j, fradius);
+        const float x = t.interp_indices[pt];
+        const intmax_t first = (intmax_t)x - a + 1;
+        for(int tap = 0; tap < taps; ++tap)
+        {
+            const float d = x - (first + tap);
+            t.interp_weights[pt * (size_t)taps + tap] = (std::abs(d) < width) ? sinc(d) * sinc(d / width) : 0.0f;
+        }
     }
 }
 
@@ -172,7 +183,7 @@ void build_interp(Tables &t, unsigned sz)
     for(auto i = 0u; i < sz; ++i)
     {
         const float pos = (c.mirror_freq_axis ? i * 2.0f : (float)i) / (float)(sz - 1);
-        const float v = c.log_scale ? log_interp(lowbin, highbin, pos) : std_lerp(lowbin, highbin, pos);
+        const float v = c.log_scale ? geo_lerp(lowbin, highbin, pos) : std_lerp(lowbin, highbin, pos);
         t.interp_indices[i] = std::clamp(v, lowbin, highbin);
     }
 
