@@ -18,7 +18,9 @@
  *   - one engine handle is externally serialised (the plugin holds m_mtx around tick/render/update,
  *     src/source.cpp:1326,1348,1079); different handles may be used concurrently from different threads.
  *   - data pointers in a wf_batch may be HOST or DEVICE pointers (all of one kind per call, detected with
- *     cudaPointerGetAttributes).  Host buffers are staged through pinned memory inside the call.
+ *     cudaPointerGetAttributes).  Host buffers are copied to / from device staging buffers inside the call, chunked so that
+ *     H2D, kernel and D2H overlap — which needs page-locked (pinned) caller buffers; pageable ones work but serialise.
+ *     Small batches in device-mapped pinned memory (wf_host_alloc) are processed in place, without copies (live ticks).
  *   - the engine owns all device memory (tables, per-stream EMA state, staging); the caller owns pcm/out.
  *   - there is no CPU fallback: without a CUDA device wf_create fails with WF_ERR_NO_DEVICE.
  */
@@ -203,6 +205,14 @@ int wf_set_state(wf_engine *e, int32_t first_stream, int32_t count, const float 
  * out_points-shaped ([..][num_points]) buffer, `row_len` its innermost length.  Device or host pointers. */
 int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_frames, int32_t row_len,
                       const float *peak, float target_db, float max_gain, void *cuda_stream);
+
+/* Page-locked, device-mapped host memory for the live path (≙ the plugin's AlignedBuffer for m_fft_input / m_decibels,
+ * src/aligned_buffer.hpp:30-80, but visible to the GPU).  When EVERY buffer of a small batch (at most 1 MiB of PCM) lives in
+ * memory from wf_host_alloc (or on the device), wf_process* launches the kernel directly on those buffers — no staging
+ * copies: one launch + one synchronisation per tick.  Pageable host buffers keep working (staged, chunked, overlapped).
+ * Returns NULL on failure; wf_host_free(NULL) is a no-op. */
+void *wf_host_alloc(size_t bytes);
+void wf_host_free(void *p);
 
 /* Number of kernel launches this engine has issued (bench.py reports it as gpu_launches). */
 int64_t wf_launch_count(const wf_engine *e);

@@ -15,6 +15,11 @@
 #include "source.hpp"
 #include "settings.hpp"
 #include "obs_stub_hooks.h"
+#ifdef WFREF_WITH_CUDA
+// libwaveform_ref_cuda.so only: the product's plugin-side binding compiled against the same unmodified reference sources
+// (waveform_b200/host/source_cuda.hpp), so that the seam of INTEGRATION.md §1 is a compiled, tested artefact.
+#include "source_cuda.hpp"
+#endif
 
 #include <algorithm>
 #include <cstring>
@@ -131,7 +136,8 @@ struct Ref {
 
 extern "C" {
 
-// impl: 0 = WAVSourceGeneric (parity target), 1 = WAVSourceAVX, 2 = WAVSourceAVX2
+// impl: 0 = WAVSourceGeneric (parity target), 1 = WAVSourceAVX, 2 = WAVSourceAVX2,
+//       3 = WAVSourceCUDA (libwaveform_ref_cuda.so only; NULL elsewhere)
 void *wfref_create(int impl, uint32_t sample_rate, int channels, uint32_t fps_num, uint32_t fps_den)
 {
     std::call_once(g_register_once, [] { WAVSource::register_source(); });
@@ -151,6 +157,11 @@ void *wfref_create(int impl, uint32_t sample_rate, int channels, uint32_t fps_nu
         std::lock_guard<std::mutex> lk(g_update_mtx);
         switch(impl)
         {
+#ifdef WFREF_WITH_CUDA
+        case 3: r->probe = std::make_unique<Probe<WAVSourceCUDA>>(nullptr); break;
+#else
+        case 3: wfstub_data_destroy(r->settings); delete r; return nullptr;
+#endif
         case 2: r->probe = std::make_unique<Probe<WAVSourceAVX2>>(nullptr); break;
         case 1: r->probe = std::make_unique<Probe<WAVSourceAVX>>(nullptr); break;
         default: r->probe = std::make_unique<Probe<WAVSourceGeneric>>(nullptr); break;

@@ -17,24 +17,35 @@ import numpy as np
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "_ref" / "libwaveform_ref.so"
+# The same unmodified reference objects + the product's plugin-side binding (waveform_b200/host/source_cuda.hpp:
+# WAVSourceCUDA, impl 3).  A separate library on purpose: the CPU baseline / oracle (LIB_PATH) never loads the product.
+CUDA_LIB_PATH = _HERE / "_ref" / "libwaveform_ref_cuda.so"
 
-IMPL_GENERIC, IMPL_AVX, IMPL_AVX2 = 0, 1, 2
+IMPL_GENERIC, IMPL_AVX, IMPL_AVX2, IMPL_CUDA = 0, 1, 2, 3
 
 _lib = None
+_lib_cuda = None
 
 
 def available() -> bool:
     return LIB_PATH.exists()
 
 
-def lib():
-    global _lib
-    if _lib is not None:
+def cuda_seam_available() -> bool:
+    return CUDA_LIB_PATH.exists()
+
+
+def lib(cuda: bool = False):
+    global _lib, _lib_cuda
+    if cuda and _lib_cuda is not None:
+        return _lib_cuda
+    if not cuda and _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = CUDA_LIB_PATH if cuda else LIB_PATH
+    if not path.exists():
         raise FileNotFoundError(
-            f"{LIB_PATH} missing: run `make -C oracle/ref_build -j8` where /root/reference exists")
-    L = C.CDLL(str(LIB_PATH))
+            f"{path} missing: run `make -C oracle/ref_build -j8` where /root/reference exists")
+    L = C.CDLL(str(path))
     vp, f32p, i32p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
     L.wfref_create.restype = vp
     L.wfref_create.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]
@@ -78,7 +89,10 @@ def lib():
                                  C.c_int, C.POINTER(C.c_ubyte)]
     L.wfref_run_wave.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte)]
     L.wfref_run_meter.argtypes = [vp, f32p, f32p, C.c_int, C.c_int, C.c_float, f32p, f32p, C.POINTER(C.c_ubyte), f32p]
-    _lib = L
+    if cuda:
+        _lib_cuda = L
+    else:
+        _lib = L
     return L
 
 
@@ -91,8 +105,10 @@ class RefSource:
 
     def __init__(self, settings: dict | None = None, impl: int = IMPL_GENERIC, sample_rate: int = 48000,
                  channels: int = 2, fps: tuple[int, int] = (60, 1)):
-        self.L = lib()
+        self.L = lib(cuda=(impl == IMPL_CUDA))
         self.h = self.L.wfref_create(impl, sample_rate, channels, fps[0], fps[1])
+        if not self.h:
+            raise RuntimeError(f"wfref_create(impl={impl}) failed")
         self.sample_rate = sample_rate
         self.channels = channels
         if settings:

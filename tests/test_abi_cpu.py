@@ -172,3 +172,20 @@ def test_hostbind_parses_sysfs(tmp_path):
     assert hostbind.numa_node_of_pci("0000:1b:00.0", sysfs=str(tmp_path)) is None
     info = hostbind.bind_to_gpu_node(0, sysfs=str(tmp_path))   # no CUDA device here: reports why, never raises
     assert info["bound"] is False and info["why"]
+
+
+def test_plugin_binding_compiles_against_the_unmodified_reference():
+    """waveform_b200/host/source_cuda.hpp (WAVSourceCUDA) is compiled against the reference's own source.cpp by
+    oracle/ref_build (libwaveform_ref_cuda.so).  Without a GPU the engine refuses to start — loudly, through the plugin's
+    log — and tick_spectrum() is a no-op: there is no CPU fallback behind the seam either."""
+    import torch
+    from oracle import refbind
+
+    if not refbind.cuda_seam_available():
+        pytest.skip("oracle/_ref/libwaveform_ref_cuda.so not built (needs /root/reference)")
+    src = refbind.RefSource({"fft_size": 2048, "window": "hann"}, impl=refbind.IMPL_CUDA, channels=1)
+    assert src.fft_size == 2048
+    if not torch.cuda.is_available():
+        x = (0.1 * np.random.default_rng(0).standard_normal((1, 8192))).astype(np.float32)
+        r = src.run_stft(x, 3, 2048)
+        assert (r["db"] == src.db_min).all()      # nothing computed: no device, no fallback

@@ -14,7 +14,7 @@ from helpers import synth_pcm
 
 PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 print("== rank 1: non-power-of-two sizes, device-resident, S=4096 streams x T=16 ticks, hop=N")
-for N in (800, 1920, 2000, 4160):
+for N in (800, 720, 960, 1600, 1920, 2000, 4160):
     S, T = 4096, 16
     eng = Engine({"fft_size": N, "window": "hann"}, channels=1, max_streams=S)
     pcm = (torch.rand((S, 1, T * N), device="cuda") - 0.5) * 0.5
@@ -31,21 +31,27 @@ for N in (800, 1920, 2000, 4160):
     b = S * T * (N * 4 + N // 2 * 4)
     print(f"  N={N:5d}: {S*T/ms/1e3:8.2f} M frames/s  {ms*1e3:8.1f} us/launch  {b/ms/1e6:7.1f} GB/s  frac_of_measured_hbm {b/ms/1e6/PEAK:.3f}")
 
-print("== rank 2: live tick latency (1 stereo source, N=4096, host buffers, wf_process blocking)")
+print("== rank 2: live tick latency (1 stereo source, N=4096): capture_audio + tick through the plugin's own code, per tick")
 N = 4096
-eng = Engine({"fft_size": N, "channel_mode": "stereo"}, channels=2, max_streams=1)
-x = synth_pcm(1, 2, N)
-lat = []
-for i in range(300):
-    t0 = time.perf_counter(); eng.process(x, 1, N); lat.append(time.perf_counter() - t0)
-lat = np.array(lat[50:]) * 1e6
-print(f"  wf_process per tick: median {np.median(lat):.1f} us  p95 {np.percentile(lat,95):.1f} us  (includes ctypes + 2 pageable copies + launch)")
 try:
     from oracle import refbind
-    for impl, name in ((refbind.IMPL_GENERIC, "generic"), (refbind.IMPL_AVX2, "AVX2")):
-        r = refbind.RefSource({"fft_size": N, "channel_mode": "stereo"}, impl=impl, channels=2)
-        pcm = synth_pcm(1, 2, 801 * 800 + N)[0]
-        t0 = time.perf_counter(); r.run_stft(pcm, 800, 800, want_db=False); dt = time.perf_counter() - t0
-        print(f"  reference WAVSource{name}::tick (capture+tick, 1 core): {dt/800*1e6:.1f} us per tick")
+    impls = [(refbind.IMPL_GENERIC, "WAVSourceGeneric (reference, 1 core)"), (refbind.IMPL_AVX2, "WAVSourceAVX2    (reference, 1 core)")]
+    if refbind.cuda_seam_available():
+        impls.append((refbind.IMPL_CUDA, "WAVSourceCUDA    (this repo: host/source_cuda.hpp -> libwfstft.so, zero-copy pinned staging)"))
+    for N in (4096, 2048):
+        print(f"  -- N={N}")
+        for impl, name in impls:
+            r = refbind.RefSource({"fft_size": N, "channel_mode": "stereo"}, impl=impl, channels=2)
+            pcm = synth_pcm(1, 2, 1001 * 800 + N)[0]
+            r.run_stft(pcm, 200, 800, want_db=False)   # warm-up
+            t0 = time.perf_counter(); r.run_stft(pcm[:, 200 * 800:], 800, 800, want_db=False); dt = time.perf_counter() - t0
+            print(f"  {name}: {dt/800*1e6:.1f} us per tick")
 except Exception as ex:
     print("  reference unavailable:", ex)
+eng = Engine({"fft_size": 4096, "channel_mode": "stereo"}, channels=2, max_streams=1)
+x = synth_pcm(1, 2, 4096)
+lat = []
+for i in range(300):
+    t0 = time.perf_counter(); eng.process(x, 1, 4096); lat.append(time.perf_counter() - t0)
+lat = np.array(lat[50:]) * 1e6
+print(f"  (python Engine.process, pageable numpy buffers, staged copies: median {np.median(lat):.1f} us  p95 {np.percentile(lat,95):.1f} us)")

@@ -69,6 +69,10 @@ struct wf_engine {
     size_t s_scratch_cap = 0;
     size_t s_pcm_cap = 0, s_out_db_cap = 0, s_out_points_cap = 0, s_rms_cap = 0, s_peak_cap = 0, s_skip_cap = 0,
            s_silent_cap = 0;
+    // zero-copy verdict of the last host-pointer batch (live ticks reuse the same buffers every call)
+    const void *zc_ptrs[9] = {};
+    bool zc_ok = false, zc_valid = false;
+    bool zero_copy = true; // WF_ZERO_COPY=0: always stage host buffers through device memory
     // copy/compute pipeline for host-pointer batches
     static constexpr int kMaxChunks = 16;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -177,6 +181,22 @@ bool supported_fft_size(int n)
     if(!make_any_plan(n, &pl))
         return false;
     return n <= 65536; // sizes whose work buffers exceed shared memory run from a global (L2) scratch
+}
+
+// 0 = pageable host (or unknown), 1 = device / managed, 2 = page-locked host memory the device can address directly
+int ptr_kind(const void *p)
+{
+    cudaPointerAttributes a{};
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    if(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)
+        return 1;
+    if(a.type == cudaMemoryTypeHost && a.devicePointer == p) // unified addressing: the same pointer is valid on the device
+        return 2;
+    return 0;
 }
 
 bool is_device_ptr(const void *p)
@@ -550,6 +570,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         const char *tw = getenv("WF_TEAM_W");
         if(tw)
             e->team_w = atoi(tw);
+        const char *zc = getenv("WF_ZERO_COPY");
+        e->zero_copy = !(zc && zc[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
         e->lazy_hold = !(lh && lh[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
@@ -893,8 +915,33 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
 
     WF_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-    const bool dev_ptrs = is_device_ptr(b->pcm);
     const size_t S = (size_t)b->n_streams, T = (size_t)b->n_frames;
+    bool dev_ptrs = false;
+    {
+        // Live ticks (one source, one frame: tens of KB) in page-locked, device-mapped host buffers (wf_host_alloc) skip the
+        // staging copies altogether: the kernel reads the frame and writes the spectrum over PCIe itself, so a tick costs one
+        // launch + one synchronisation.  Every buffer of the batch must be device-addressable for that.
+        const void *ptrs[9] = {b->pcm, b->input_rms, b->skip_mask, b->out_db, b->out_points, b->out_silent, b->out_peak, b->out_pixels,
+                               b->out_min};
+        if(e->zc_valid && memcmp(ptrs, e->zc_ptrs, sizeof(ptrs)) == 0 && e->zc_ok)
+            dev_ptrs = true; // same buffers as the last call, already classified
+        else
+        {
+            const int kpcm = ptr_kind(b->pcm);
+            dev_ptrs = (kpcm == 1);
+            bool zc = false;
+            if(kpcm == 2 && e->zero_copy && S * T * (size_t)cc * (size_t)N * sizeof(float) <= (1u << 20))
+            {
+                zc = true;
+                for(int i = 1; i < 9 && zc; ++i)
+                    zc = (ptrs[i] == nullptr) || (ptr_kind(ptrs[i]) != 0);
+            }
+            memcpy(e->zc_ptrs, ptrs, sizeof(ptrs));
+            e->zc_ok = zc;
+            e->zc_valid = true;
+            dev_ptrs = dev_ptrs || zc;
+        }
+    }
 
     if(dev_ptrs)
     {
@@ -1216,6 +1263,23 @@ int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_fr
         WF_CUDA(e, cudaStreamSynchronize(st));
     }
     return WF_OK;
+}
+
+void *wf_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if(bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void wf_host_free(void *p)
+{
+    if(p)
+        cudaFreeHost(p);
 }
 
 int64_t wf_launch_count(const wf_engine *e) { return e ? e->launches : 0; }

@@ -43,7 +43,7 @@ EXPORTS = [
     "wf_abi_version", "wf_strerror", "wf_last_error", "wf_config_init", "wf_create", "wf_destroy", "wf_get_info",
     "wf_get_table", "wf_gravity", "wf_process", "wf_process_async", "wf_synchronize", "wf_reset_state",
     "wf_get_state", "wf_set_state", "wf_peak_normalize", "wf_launch_count", "wf_last_kernel_ms", "wf_last_kernel_name",
-    "wf_preview_table",
+    "wf_host_alloc", "wf_host_free", "wf_preview_table",
     "wf_meter_config_init", "wf_meter_create", "wf_meter_destroy", "wf_meter_last_error", "wf_meter_window",
     "wf_meter_process", "wf_meter_process_async", "wf_meter_reset", "wf_meter_launch_count", "wf_meter_last_kernel_ms",
     "wf_wave_config_init", "wf_wave_create", "wf_wave_destroy", "wf_wave_last_error", "wf_wave_process",
@@ -170,6 +170,9 @@ def load_library():
     L.wf_launch_count.argtypes = [vp]
     L.wf_last_kernel_ms.restype = C.c_float
     L.wf_last_kernel_ms.argtypes = [vp]
+    L.wf_host_alloc.restype = C.c_void_p
+    L.wf_host_alloc.argtypes = [C.c_size_t]
+    L.wf_host_free.argtypes = [vp]
     L.wf_last_kernel_name.restype = C.c_char_p
     L.wf_last_kernel_name.argtypes = [vp]
     L.wf_meter_config_init.argtypes = [C.POINTER(WfMeterConfig)]
