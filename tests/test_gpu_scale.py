@@ -304,3 +304,43 @@ def test_fp64_arbiter_gpu_and_reference_errors():
     # and in dB on the bins that matter (within 60 dB of the frame peak)
     strong = lin(truth) >= peak * 1e-3
     assert np.abs(got - truth)[strong].max() < 1e-3
+
+
+WARP2_SIZES = [400, 720, 800, 960, 1456, 1600, 640, 1152, 1280, 1536, 1792, 1920]
+
+
+@pytest.mark.parametrize("N", WARP2_SIZES)
+def test_warp2_nonpow2_sizes_parity(N, monkeypatch):
+    """wf_warp2.cuh (two register-DFT passes per warp: radix 2/3/5/7/13 butterflies) for the plugin's non-power-of-two
+    sizes: parity against the oracle (plain and all-options settings, gate, call boundary) and agreement with the
+    first-generation any-N kernel."""
+    import torch
+    from waveform_b200 import Engine
+
+    for settings in ({"fft_size": N, "window": "hann", "gravity": 0.3, "floor": -40},
+                     {"fft_size": N, "window": "blackman_harris", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0,
+                      "fast_peaks": True, "temporal_smoothing": "tv_exp_moving_avg", "gravity": 0.5}):
+        S, T = 37, 26
+        pcm = synth_pcm(S, 1, T * N, zero_frames=[(1, 3, 7), (2, 0, 26), (5, 4, 26)], frame_len=N, hop=N)
+        pcm[5, :, 20 * N: 21 * N] = 0.1
+        x = torch.from_numpy(pcm).cuda()
+        eng = Engine(settings, channels=1, max_streams=S)
+        a = eng.process(x[:, :, : 9 * N].contiguous(), 9, N)
+        b = eng.process(x[:, :, 9 * N:].contiguous(), T - 9, N)
+        torch.cuda.synchronize()
+        assert eng.last_kernel_name().startswith("stft_warp2_kernel<"), eng.last_kernel_name()
+        got = torch.cat([a["db"], b["db"]], dim=1).cpu().numpy()
+        sil = torch.cat([a["silent"], b["silent"]], dim=1).cpu().numpy()
+        ref_db, _, ref_sil = _oracle_rows(settings, 1, pcm, T, N)
+        rep = parity_report(got, ref_db, db_min=eng.db_min)
+        assert rep["ok"] and rep["normwise"] < 1e-6, (settings, rep)
+        assert np.array_equal(sil, ref_sil) and ref_sil.sum() > 10
+        monkeypatch.setenv("WF_WARP2", "0")
+        old = Engine(settings, channels=1, max_streams=S)
+        c = old.process(x, T, N)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("WF_WARP2")
+        assert old.last_kernel_name().startswith("stft_anyn"), old.last_kernel_name()
+        rep2 = parity_report(got, c["db"].cpu().numpy(), db_min=eng.db_min)
+        assert rep2["ok"], rep2
+        assert np.array_equal(sil, c["silent"].cpu().numpy())

@@ -22,6 +22,7 @@
 #include "wf_wide.hpp"
 #include "wf_v3.hpp"
 #include "wf_team2048.hpp"
+#include "wf_warp2.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -38,6 +39,7 @@ struct wf_engine {
     int64_t launches = 0;
     std::string last_kernel;    // name of the spectrum kernel the most recent launch_range dispatched to (wf_last_kernel_name)
     bool hold_implicit = false; // some stream may carry flags bit 3 (m_decibels mirror left implicit by the N=2048 kernel)
+    bool use_warp2 = true;      // WF_WARP2=0: non-power-of-two sizes stay on the first-generation any-N kernel (A/B tests)
     bool lazy_hold = true;      // WF_LAZY_HOLD=0: always write the mirror (A/B tests)
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
@@ -572,6 +574,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->team_w = atoi(tw);
         const char *zc = getenv("WF_ZERO_COPY");
         e->zero_copy = !(zc && zc[0] == '0');
+        const char *w2 = getenv("WF_WARP2");
+        e->use_warp2 = !(w2 && w2[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
         e->lazy_hold = !(lh && lh[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
@@ -887,6 +891,20 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         const int rc = materialize_hold(e, st); // the other kernels read hold_db as it is
         if(rc)
             return rc;
+    }
+    // Non-power-of-two sizes with a compiled two-pass plan (wf_warp2.cuh): same launch shape as the N=2048 kernel.
+    const bool warp2_ok = e->use_warp2 && warp2_supported(N) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points &&
+                          !kp.out_pixels && !kp.out_min && aligned16;
+    if(warp2_ok)
+    {
+        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+        int wpc = 16, grid = 1;
+        fast2048_geometry(kp.n_streams, e->sm_count, 16, &wpc, &grid);
+        const char *name = "";
+        WF_CUDA(e, warp2_launch(N, x, kp, grid, wpc, st, e->use_pdl, e->device, &name));
+        e->launches++;
+        e->last_kernel = std::string(name) + " N=" + std::to_string(N) + " grid " + std::to_string(grid) + " x " + std::to_string(wpc) + " warps";
+        return WF_OK;
     }
     return (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
 }

@@ -274,5 +274,172 @@ __device__ __forceinline__ void dft_bitrev(c64 (&v)[R])
     dif_block<R, 0, R>(v);
 }
 
+
+// ---- mixed-radix register DFT of any length R <= 32 (compile-time plan) ---------------------------------------------
+// Decimation in frequency by the smallest prime factor r of R (R = r*m): for every j < m a radix-r butterfly on
+// v[j + m*i], i < r, its output t multiplied by W_R^(j*t) and stored at v[t*m + j]; then the r blocks of length m
+// recursively.  Afterwards X[k] == v[perm_mixed(R, k)], perm_mixed(R, k) = (k % r)*m + perm_mixed(m, k / r)
+// (for powers of two this is the bit reversal of dft_bitrev).  Radix 2 is add/sub; an odd prime p uses the symmetric form
+//   X_k, X_(p-k) = (a0 + sum_j cos(2 pi jk/p)(a_j + a_(p-j)))  -/+  i (sum_j sin(2 pi jk/p)(a_j - a_(p-j)))
+// with compile-time constants: (p-1)^2/2 packed FMAs — radix 3, 5, 7, 11, 13 from one template.  These are the "register
+// butterflies for radix 3/5" the plugin's non-power-of-two sizes need (800 = 2^5 5^2, 1920 = 2^7 3 5, ...).
+constexpr int smallest_factor(int n)
+{
+    for(int f = 2; f * f <= n; ++f)
+        if(n % f == 0)
+            return f;
+    return n;
+}
+constexpr int perm_mixed(int R, int k)
+{
+    if(R <= 1)
+        return 0;
+    const int r = smallest_factor(R), m = R / r;
+    return (k % r) * m + perm_mixed(m, k / r);
+}
+
+__device__ __forceinline__ c64 mul_pos_i(c64 a) // a * (+i) = (-im, re)
+{
+    float x, y;
+    split(a, x, y);
+    return make(-y, x);
+}
+__device__ __forceinline__ c64 neg(c64 a)
+{
+    float x, y;
+    split(a, x, y);
+    return make(-x, -y);
+}
+// multiply by W_L^J for any 0 <= J < L (more special cases than mul_tw: -1 and +i)
+template<int J, int L>
+__device__ __forceinline__ c64 mul_tw_any(c64 a)
+{
+    if constexpr(J % L == 0)
+        return a;
+    else if constexpr(2 * (J % L) == L)
+        return neg(a);
+    else if constexpr(4 * (J % L) == L)
+        return mul_neg_i(a);
+    else if constexpr(4 * (J % L) == 3 * L)
+        return mul_pos_i(a);
+    else
+    {
+        constexpr float c = (float)cx::cos2pi(J % L, L);
+        constexpr float s = -(float)cx::sin2pi(J % L, L);
+        return fma(swap(a), make(-s, s), mul(a, make(c, c)));
+    }
+}
+
+// radix-P butterfly (P an odd prime) on a[0..P): a[t] = sum_i a[i] W_P^(i t)
+template<int P, int K, int J>
+__device__ __forceinline__ void prime_acc(const c64 (&s)[P], const c64 (&d)[P], c64 &m, c64 &n)
+{
+    if constexpr(J <= (P - 1) / 2)
+    {
+        constexpr float c = (float)cx::cos2pi((J * K) % P, P);
+        constexpr float sn = (float)cx::sin2pi((J * K) % P, P);
+        m = fma(s[J], make(c, c), m);
+        n = (J == 1) ? mul(d[J], make(sn, sn)) : fma(d[J], make(sn, sn), n);
+        prime_acc<P, K, J + 1>(s, d, m, n);
+    }
+}
+template<int P, int K>
+__device__ __forceinline__ void prime_out(const c64 a0, const c64 (&s)[P], const c64 (&d)[P], c64 (&out)[P])
+{
+    if constexpr(K <= (P - 1) / 2)
+    {
+        c64 m = a0, n = 0ull;
+        prime_acc<P, K, 1>(s, d, m, n);
+        const c64 in = mul_neg_i(n); // -i n
+        out[K] = add(m, in);
+        out[P - K] = sub(m, in);
+        prime_out<P, K + 1>(a0, s, d, out);
+    }
+}
+template<int P>
+__device__ __forceinline__ void bfly_prime(c64 (&a)[P])
+{
+    c64 s[P], d[P], out[P];
+    c64 x0 = a[0];
+#pragma unroll
+    for(int j = 1; j <= (P - 1) / 2; ++j)
+    {
+        s[j] = add(a[j], a[P - j]);
+        d[j] = sub(a[j], a[P - j]);
+        x0 = add(x0, s[j]);
+    }
+    prime_out<P, 1>(a[0], s, d, out);
+    a[0] = x0;
+#pragma unroll
+    for(int k = 1; k < P; ++k)
+        a[k] = out[k];
+}
+
+template<int R, int BASE, int RMAX>
+__device__ __forceinline__ void dif_mixed(c64 (&v)[RMAX]);
+
+// one DIF step of the block [BASE, BASE + r*m): butterflies j = J .. m-1
+template<int r, int m, int BASE, int J, int T, int RMAX>
+__device__ __forceinline__ void dif_twiddle(c64 (&v)[RMAX])
+{
+    if constexpr(T < r)
+    {
+        v[BASE + T * m + J] = mul_tw_any<J * T, r * m>(v[BASE + T * m + J]);
+        dif_twiddle<r, m, BASE, J, T + 1, RMAX>(v);
+    }
+}
+template<int r, int m, int BASE, int J, int RMAX>
+__device__ __forceinline__ void dif_step(c64 (&v)[RMAX])
+{
+    if constexpr(J < m)
+    {
+        if constexpr(r == 2)
+        {
+            const c64 a = v[BASE + J], c = v[BASE + J + m];
+            v[BASE + J] = add(a, c);
+            v[BASE + J + m] = mul_tw_any<J, 2 * m>(sub(a, c));
+        }
+        else
+        {
+            c64 a[r];
+#pragma unroll
+            for(int i = 0; i < r; ++i)
+                a[i] = v[BASE + J + m * i];
+            bfly_prime<r>(a);
+#pragma unroll
+            for(int t = 0; t < r; ++t)
+                v[BASE + t * m + J] = a[t];
+            dif_twiddle<r, m, BASE, J, 1, RMAX>(v);
+        }
+        dif_step<r, m, BASE, J + 1, RMAX>(v);
+    }
+}
+template<int r, int m, int BASE, int T, int RMAX>
+__device__ __forceinline__ void dif_children(c64 (&v)[RMAX])
+{
+    if constexpr(T < r)
+    {
+        dif_mixed<m, BASE + T * m, RMAX>(v);
+        dif_children<r, m, BASE, T + 1, RMAX>(v);
+    }
+}
+template<int R, int BASE, int RMAX>
+__device__ __forceinline__ void dif_mixed(c64 (&v)[RMAX])
+{
+    if constexpr(R >= 2)
+    {
+        constexpr int r = smallest_factor(R), m = R / r;
+        dif_step<r, m, BASE, 0, RMAX>(v);
+        if constexpr(m >= 2)
+            dif_children<r, m, BASE, 0, RMAX>(v);
+    }
+}
+// In-place forward DFT of v[0..R) (R <= RMAX): afterwards X[k] == v[perm_mixed(R, k)].
+template<int R, int RMAX>
+__device__ __forceinline__ void dft_mixed(c64 (&v)[RMAX])
+{
+    dif_mixed<R, 0, RMAX>(v);
+}
+
 } // namespace pk
 } // namespace wf
