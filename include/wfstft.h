@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define WF_ABI_VERSION 1
+#define WF_ABI_VERSION 2
 
 typedef enum wf_status {
     WF_OK = 0,
@@ -150,6 +150,10 @@ typedef struct wf_batch {
     float *out_pixels;         /* optional [n_streams][n_frames][display_channels][num_points]: what render_curve /
                                   render_bars leave in m_interp_bufs — pixel heights after lerp/clamp and mirroring */
     float *out_min;            /* optional [n_streams][n_frames][2]: (miny, minpos) of the tick (pulse colouring) */
+    const float *frame_seconds; /* optional HOST array [n_frames]: the `seconds` argument of each tick (src/source.cpp:1324).
+                                  Only TVEXPONENTIAL smoothing looks at it: gravity = exp(-seconds / (gravity * 0.1934...))
+                                  is then evaluated per tick as get_gravity() does (src/source.hpp:301-312), so a batch
+                                  recorded with jittering frame times replays exactly.  NULL: `seconds` for every tick. */
 } wf_batch;
 
 typedef struct wf_engine wf_engine;

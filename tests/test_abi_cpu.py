@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in wfstft.h but not exported"
     assert sorted(EXPORTS) == declared
-    assert L.wf_abi_version() == 1
+    assert L.wf_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):

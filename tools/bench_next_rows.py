@@ -55,3 +55,24 @@ for i in range(300):
     t0 = time.perf_counter(); eng.process(x, 1, 4096); lat.append(time.perf_counter() - t0)
 lat = np.array(lat[50:]) * 1e6
 print(f"  (python Engine.process, pageable numpy buffers, staged copies: median {np.median(lat):.1f} us  p95 {np.percentile(lat,95):.1f} us)")
+
+# where a live tick's time goes: the C call alone (no plugin plumbing), zero-copy pinned buffers from wf_host_alloc
+import ctypes as C
+for (N, ch, mode) in ((4096, 2, "stereo"), (2048, 1, "mono")):
+    e = Engine({"fft_size": N, "channel_mode": mode}, channels=ch, max_streams=1)
+    L = e.L
+    cc, dch, B = e.capture_channels, e.display_channels, e.bins
+    pin = L.wf_host_alloc(cc * N * 4); pout = L.wf_host_alloc(dch * B * 4); pfl = L.wf_host_alloc(16)
+    src = synth_pcm(1, cc, N)[0].ravel()
+    C.memmove(pin, src.ctypes.data, src.nbytes)
+    wall, kern = [], []
+    for i in range(400):
+        t0 = time.perf_counter()
+        e.process_raw(pin, 1, 1, N, cc * N, N, out_db=pout, out_silent=pfl + 1, skip_mask=pfl)
+        wall.append(time.perf_counter() - t0)
+        if i % 8 == 0:
+            kern.append(e.last_kernel_ms() * 1e3)
+    wall = np.array(wall[50:]) * 1e6
+    print(f"  wf_process alone, zero-copy, N={N} {mode}: wall median {np.median(wall):.1f} us p95 {np.percentile(wall,95):.1f} us; "
+          f"kernel (events) median {np.median(kern):.1f} us; {e.last_kernel_name()}")
+    L.wf_host_free(pin); L.wf_host_free(pout); L.wf_host_free(pfl)

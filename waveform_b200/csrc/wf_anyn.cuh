@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
 
     for(int t = 0; t < T; ++t)
     {
+        const float2 gt = (p.g_tab != nullptr) ? __ldg(p.g_tab + t) : make_float2(p.g, p.g2); // gravity of this tick (src/source.hpp:301-312)
         const bool skip_all = (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
         bool proc[2] = {false, false};
         unsigned silent_channels = 0;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kAnyThreads) stft_anyn_kernel(const __grid_con
                         float oldval = st[k];
                         if(p.fast_peaks)
                             oldval = fmaxf(mag, oldval);
-                        mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+                        mag = __fadd_rn(__fmul_rn(gt.x, oldval), __fmul_rn(gt.y, mag));
                     }
                     st[k] = mag;
                 }

@@ -66,6 +66,9 @@ struct wf_engine {
     float *s_pcm = nullptr, *s_out_db = nullptr, *s_out_points = nullptr, *s_rms = nullptr, *s_peak = nullptr;
     unsigned char *s_skip = nullptr, *s_silent = nullptr;
     float *s_px = nullptr, *s_min = nullptr;
+    float *s_gtab = nullptr; // [n_frames][2] per-tick (g, 1-g) of a TV-exponential batch with frame_seconds
+    size_t s_gtab_cap = 0;
+    std::vector<float> h_gtab;
     size_t s_px_cap = 0, s_min_cap = 0;
     float *s_scratch = nullptr; // any-N kernel work buffers when N/2 complex points x 2 exceed shared memory
     size_t s_scratch_cap = 0;
@@ -271,7 +274,7 @@ int dispatch_n(wf_engine *e, const KParams &kp, cudaStream_t st, size_t extra)
         const bool display = kp.out_points || kp.out_pixels || kp.out_min;
         if(e->use_v3 && e->d_tw1 != nullptr && v3_smem_bytes(e->tab.N, kp.dch, kp.scratch_q, display, CC, 8) <= 227 * 1024)
         {
-            const bool feat = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask;
+            const bool feat = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.g_tab;
             const int x = feat ? 3 : (kp.out_peak ? 1 : 0);
             const int r = pick_v3_r(e, kp);
             WF_CUDA(e, v3_launch(e->tab.N, CC, r, x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, display, e->device));
@@ -653,7 +656,7 @@ void wf_destroy(wf_engine *e)
     }
     void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_tw0, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
-                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min};
+                    e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min, e->s_gtab};
     for(void *p : ptrs)
         if(p)
             cudaFree(p);
@@ -764,7 +767,7 @@ int64_t wf_preview_table(const wf_config *cfg, int which, float *out, int64_t ca
 // offset to stream 0 of the batch.
 static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0, int count, const float *pcm,
                         const float *rms, const unsigned char *skip, float *out_db, float *out_points,
-                        unsigned char *silent, float *out_peak, float *px_dev, float *min_dev)
+                        unsigned char *silent, float *out_peak, float *px_dev, float *min_dev, const float *g_tab_dev)
 {
     const Tables &t = e->tab;
     const int cc = t.cfg.capture_channels, dch = t.display_channels, och = t.output_channels, B = t.B, N = t.N;
@@ -797,6 +800,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     kp.coef_half = (2.0f / t.window_sum) * 0.5f; // mag_coefficient/2: the split pass leaves 2*X (src/source_generic.cpp:110)
     kp.g = (t.cfg.tsmoothing == WF_TSMOOTH_NONE) ? 0.0f : gravity_for(t.cfg, b->seconds);
     kp.g2 = 1.0f - kp.g;
+    kp.g_tab = reinterpret_cast<const float2 *>(g_tab_dev);
     kp.tsmooth = t.cfg.tsmoothing != WF_TSMOOTH_NONE;
     kp.fast_peaks = t.cfg.fast_peaks;
     kp.stereo = t.cfg.stereo;
@@ -855,7 +859,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
                          !kp.out_min && aligned16 && !e->force_generic;
     if(fast_ok)
     {
-        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         kp.lazy_hold = e->lazy_hold ? 1 : 0;
         if(kp.lazy_hold)
             e->hold_implicit = true;
@@ -897,7 +901,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
                           !kp.out_pixels && !kp.out_min && aligned16;
     if(warp2_ok)
     {
-        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak;
+        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         int wpc = 16, grid = 1;
         fast2048_geometry(kp.n_streams, e->sm_count, 16, &wpc, &grid);
         const char *name = "";
@@ -934,6 +938,23 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
     WF_CUDA(e, cudaSetDevice(e->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
     const size_t S = (size_t)b->n_streams, T = (size_t)b->n_frames;
+    // per-tick gravity (TVEXPONENTIAL only): evaluated on the host exactly as get_gravity(seconds) does, one pair per tick
+    const float *d_gtab = nullptr;
+    if(b->frame_seconds != nullptr && t.cfg.tsmoothing == WF_TSMOOTH_TVEXPONENTIAL)
+    {
+        int rcg = ensure(e, &e->s_gtab, &e->s_gtab_cap, 2 * T);
+        if(rcg)
+            return rcg;
+        e->h_gtab.resize(2 * T);
+        for(size_t i = 0; i < T; ++i)
+        {
+            const float g = gravity_for(t.cfg, b->frame_seconds[i]);
+            e->h_gtab[2 * i] = g;
+            e->h_gtab[2 * i + 1] = 1.0f - g;
+        }
+        WF_CUDA(e, cudaMemcpyAsync(e->s_gtab, e->h_gtab.data(), 2 * T * sizeof(float), cudaMemcpyHostToDevice, st));
+        d_gtab = e->s_gtab;
+    }
     bool dev_ptrs = false;
     {
         // Live ticks (one source, one frame: tens of KB) in page-locked, device-mapped host buffers (wf_host_alloc) skip the
@@ -971,7 +992,7 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
                 return rc;
         }
         int rc = launch_range(e, b, st, 0, b->n_streams, b->pcm, b->input_rms, b->skip_mask, b->out_db, b->out_points,
-                              b->out_silent, b->out_peak, b->out_pixels, b->out_min);
+                              b->out_silent, b->out_peak, b->out_pixels, b->out_min, d_gtab);
         if(rc)
             return rc;
         WF_CUDA(e, cudaEventRecord(e->ev1, st));
@@ -1079,7 +1100,7 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         WF_CUDA(e, cudaEventRecord(e->chunk_in[c], e->s_h2d));
         WF_CUDA(e, cudaStreamWaitEvent(st, e->chunk_in[c], 0));
         if((rc = launch_range(e, b, st, s0, cnt, e->s_pcm, d_rms, d_skip, d_out_db, d_out_points, d_silent, d_peak, d_px,
-                              d_min)))
+                              d_min, d_gtab)))
             return rc;
         WF_CUDA(e, cudaEventRecord(e->chunk_k[c], st));
         WF_CUDA(e, cudaStreamWaitEvent(e->s_d2h, e->chunk_k[c], 0));

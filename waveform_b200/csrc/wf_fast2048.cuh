@@ -274,6 +274,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             }
             bool outs = true;
             float peak = -INFINITY;
+            // gravity of this tick: the call's scalar, or (EXTRA variant only) the per-tick table of a TV-exponential batch
+            const float2 gt = (EXTRA && p.g_tab != nullptr) ? __ldg(p.g_tab + t) : make_float2(p.g, p.g2);
 
             if(do_proc && !last_silent)
             {
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                         if(EXTRA && p.fast_peaks)
                             old = pk::make(fmaxf(pk::re(m), pk::re(old)), fmaxf(pk::im(m), pk::im(old)));
                         // g*old + g2*new with one fused rounding, as the reference's AVX2 path (src/source_avx2.cpp:154)
-                        m = pk::fma(pk::make(p.g, p.g), old, pk::mul(pk::make(p.g2, p.g2), m));
+                        m = pk::fma(pk::make(gt.x, gt.x), old, pk::mul(pk::make(gt.y, gt.y), m));
                     }
                     sst64[q * 32] = m;
                     float d1, d2;

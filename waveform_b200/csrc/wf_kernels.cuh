@@ -48,6 +48,7 @@ struct KParams {
     // scalars
     float coef_half;  // (2 / window_sum) / 2
     float g, g2;      // gravity, 1 - gravity
+    const float2 *g_tab; // optional [n_frames] (g, 1-g) per tick: TV-exponential smoothing with per-tick frame times
     int tsmooth;      // != 0: EMA enabled
     int fast_peaks;
     int stereo, och, dch;
@@ -656,6 +657,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA, Geo<N>::MINB) stft_fused_kernel(c
 
     for(int t = 0; t < p.n_frames; ++t)
     {
+        const float2 gt = (p.g_tab != nullptr) ? __ldg(p.g_tab + t) : make_float2(p.g, p.g2); // gravity of this tick (src/source.hpp:301-312)
         const bool skip_all = (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * p.n_frames + t] != 0);
         bool proc[2] = {false, false};
         unsigned silent_channels = 0;
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(Geo<N>::CTA, Geo<N>::MINB) stft_fused_kernel(c
                     float oldval = st[c][i];
                     if(p.fast_peaks)
                         oldval = fmaxf(mag, oldval);
-                    mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+                    mag = __fadd_rn(__fmul_rn(gt.x, oldval), __fmul_rn(gt.y, mag));
                 }
                 if(do_proc)
                     st[c][i] = mag;

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(team::kWarps * 32, 1) stft2048_team_kernel(con
                         }
                     }
                 }
+                const float2 gt = (EXTRA && p.g_tab != nullptr) ? __ldg(p.g_tab + tt) : make_float2(p.g, p.g2); // gravity of this tick
                 float *odb = p.out_db + ((size_t)s * T + tt) * B + b0;
                 float vc = 0.0f;
                 if(EXTRA && p.normalize)
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(team::kWarps * 32, 1) stft2048_team_kernel(con
                                 if(EXTRA && p.fast_peaks)
                                     old = fmaxf(mm, old);
                                 // one fused rounding, as wf_fast2048.cuh and the reference's AVX2 path (src/source_avx2.cpp:154)
-                                mm = fmaf(p.g, old, p.g2 * mm);
+                                mm = fmaf(gt.x, old, gt.y * mm);
                             }
                             st[j + u] = mm;
                         }

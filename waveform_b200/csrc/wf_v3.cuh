@@ -415,7 +415,15 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     };
     // EMA of one bin, src/source_generic.cpp:124-132
     // (without temporal smoothing the engine passes g = 0, g2 = 1: 0*old + 1*mag == mag exactly, no branch needed)
-    const float ema_g = p.g, ema_g2 = p.g2;
+    float ema_g = p.g, ema_g2 = p.g2; // per tick when the batch carries a gravity table (set_gravity below)
+    auto set_gravity = [&](int t) {
+        if(XF && p.g_tab != nullptr)
+        {
+            const float2 gt = __ldg(p.g_tab + t);
+            ema_g = gt.x;
+            ema_g2 = gt.y;
+        }
+    };
     auto ema = [&](float mag, float &state, bool do_proc) {
         float oldval = state;
         if(XF && p.fast_peaks)
@@ -612,6 +620,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         {
             // ---- one CTA per stream: FFT -> gate -> split pass -> EMA per channel, all in registers ----
             const int t = t0;
+            set_gravity(t);
             const bool skip_all = XF && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
             bool proc[2] = {false, false};
             unsigned silent_channels = 0;
@@ -724,6 +733,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             for(int f = 0; f < nf; ++f)
             {
                 const int t = t0 + f;
+                set_gravity(t);
                 const unsigned nzb = nzf[par][f];
                 const bool skip_all = XF && (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
                 bool proc[2] = {false, false};

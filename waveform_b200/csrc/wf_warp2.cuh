@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
             }
             bool outs = true;
             float peak = -INFINITY;
+            const float2 gt = (EXTRA && p.g_tab != nullptr) ? __ldg(p.g_tab + t) : make_float2(p.g, p.g2); // gravity of this tick
 
             if(do_proc && !last_silent)
             {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
                         pk::c64 old = sst64[q * 32];
                         if(EXTRA && p.fast_peaks)
                             old = pk::make(fmaxf(pk::re(m), pk::re(old)), fmaxf(pk::im(m), pk::im(old)));
-                        m = pk::fma(pk::make(p.g, p.g), old, pk::mul(pk::make(p.g2, p.g2), m));
+                        m = pk::fma(pk::make(gt.x, gt.x), old, pk::mul(pk::make(gt.y, gt.y), m));
                     }
                     sst64[q * 32] = m;
                     float d1, d2;

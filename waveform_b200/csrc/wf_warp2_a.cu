@@ -12,6 +12,8 @@ bool warp2_supported(int N)
     {
     case 400: case 720: case 800: case 960: case 1456: case 1600: // part A
     case 1920: case 640: case 1280: case 1536: case 1152: case 1792: // part B
+    case 192: case 320: case 384: case 448: case 576: case 704: case 768: case 832: case 896: // part C
+    case 1344: case 1408: case 1664: case 1728: case 880: case 480: case 528: case 352: case 288: // part D
         return true;
     default: return false;
     }

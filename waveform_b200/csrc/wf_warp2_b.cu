@@ -3,6 +3,11 @@
 
 namespace wf {
 
+cudaError_t warp2_launch_c(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+                           const char **name);
+cudaError_t warp2_launch_d(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+                           const char **name);
+
 cudaError_t warp2_launch_b(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
                            const char **name)
 {
@@ -15,8 +20,10 @@ cudaError_t warp2_launch_b(int N, bool extra, const KParams &kp, int grid, int w
         WF_WARP2_CASE(1536, 24, 32)
         WF_WARP2_CASE(1792, 28, 32)
         WF_WARP2_CASE(1920, 30, 32)
-    default: return cudaErrorInvalidValue;
+    default: break;
     }
+    const cudaError_t rc = warp2_launch_c(N, extra, kp, grid, warps, st, pdl, device, name);
+    return (rc == cudaErrorInvalidValue) ? warp2_launch_d(N, extra, kp, grid, warps, st, pdl, device, name) : rc;
 }
 
 } // namespace wf

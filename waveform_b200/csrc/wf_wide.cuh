@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(Geo<N>::TN, Geo<N>::MINB) stft_wide_kernel(con
         for(int f = 0; f < nf; ++f)
         {
             const int t = t0 + f;
+            const float2 gt = (p.g_tab != nullptr) ? __ldg(p.g_tab + t) : make_float2(p.g, p.g2); // gravity of this tick (src/source.hpp:301-312)
             const unsigned nzb = nzf[f];
             const bool skip_all = (p.skip_mask != nullptr) && (p.skip_mask[(size_t)s * T + t] != 0);
             bool proc[2] = {false, false};
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(Geo<N>::TN, Geo<N>::MINB) stft_wide_kernel(con
                         float oldval = st[c][i];
                         if(p.fast_peaks)
                             oldval = fmaxf(mag, oldval);
-                        mag = __fadd_rn(__fmul_rn(p.g, oldval), __fmul_rn(p.g2, mag));
+                        mag = __fadd_rn(__fmul_rn(gt.x, oldval), __fmul_rn(gt.y, mag));
                     }
                     if(do_proc)
                         st[c][i] = mag;

@@ -120,7 +120,7 @@ class WfBatch(C.Structure):
         ("pcm", C.c_void_p), ("stream_stride", C.c_int64), ("channel_stride", C.c_int64),
         ("input_rms", C.c_void_p), ("skip_mask", C.c_void_p),
         ("out_db", C.c_void_p), ("out_points", C.c_void_p), ("out_silent", C.c_void_p), ("out_peak", C.c_void_p),
-        ("out_pixels", C.c_void_p), ("out_min", C.c_void_p),
+        ("out_pixels", C.c_void_p), ("out_min", C.c_void_p), ("frame_seconds", C.c_void_p),
     ]
 
 
@@ -369,7 +369,8 @@ class Engine:
     # ---- processing ----
     def process_raw(self, pcm_ptr, n_streams, n_frames, hop, stream_stride, channel_stride, *, first_stream=0,
                     seconds=1.0 / 60.0, input_rms=None, skip_mask=None, out_db=None, out_points=None,
-                    out_silent=None, out_peak=None, out_pixels=None, out_min=None, stream=None, sync=True):
+                    out_silent=None, out_peak=None, out_pixels=None, out_min=None, stream=None, sync=True,
+                    frame_seconds=None):
         """Thin wrapper over wf_process / wf_process_async with raw pointers (ints)."""
         b = WfBatch()
         b.struct_size = C.sizeof(WfBatch)
@@ -380,6 +381,7 @@ class Engine:
         b.input_rms, b.skip_mask = input_rms, skip_mask
         b.out_db, b.out_points, b.out_silent, b.out_peak = out_db, out_points, out_silent, out_peak
         b.out_pixels, b.out_min = out_pixels, out_min
+        b.frame_seconds = frame_seconds  # host pointer (int) or None
         if sync and stream is None:
             self._check(self.L.wf_process(self.h, C.byref(b)))
         else:
@@ -388,7 +390,8 @@ class Engine:
             self._check(self.L.wf_process_async(self.h, C.byref(b), stream))
 
     def process(self, pcm, n_frames: int, hop: int, *, first_stream=0, seconds=1.0 / 60.0, input_rms=None,
-                skip_mask=None, want_db=True, want_points=False, want_silent=True, want_peak=False, want_pixels=False):
+                skip_mask=None, want_db=True, want_points=False, want_silent=True, want_peak=False, want_pixels=False,
+                frame_seconds=None):
         """pcm: [n_streams, capture_channels, samples] float32 — numpy (host path, staged inside the C call)
         or a CUDA torch tensor (device path, outputs are CUDA tensors)."""
         is_torch = hasattr(pcm, "data_ptr")
@@ -437,11 +440,15 @@ class Engine:
         if is_torch:
             import torch
             stream = torch.cuda.current_stream(pcm.device).cuda_stream
+        fs = None
+        if frame_seconds is not None:  # per-tick `seconds` (always a host array), see wf_batch.frame_seconds
+            fs = np.ascontiguousarray(frame_seconds, dtype=np.float32)
+            assert fs.shape == (n_frames,)
         self.process_raw(_ptr(pcm), S, n_frames, hop, cc * ns, ns, first_stream=first_stream, seconds=seconds,
                          input_rms=_ptr(input_rms), skip_mask=_ptr(skip_mask), out_db=_ptr(out.get("db")),
                          out_points=_ptr(out.get("points")), out_silent=_ptr(out.get("silent")),
                          out_peak=_ptr(out.get("peak")), out_pixels=_ptr(out.get("pixels")), out_min=_ptr(out.get("min")),
-                         stream=stream, sync=not is_torch)
+                         stream=stream, sync=not is_torch, frame_seconds=None if fs is None else fs.ctypes.data)
         return out
 
     def synchronize(self):
