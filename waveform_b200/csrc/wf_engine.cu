@@ -340,7 +340,9 @@ static void fast2048_geometry(int n_streams, int sm_count, int max_wpc, int *war
 {
     *grid = std::min(n_streams, sm_count);
     const int per_cta = (n_streams + *grid - 1) / *grid;
-    *warps_per_cta = std::max(1, std::min(max_wpc, per_cta));
+    // at least 8 warps even for one stream: the CTA prologue (tables -> shared memory) is spread over the CTA's threads, and
+    // with a single warp it dominated the latency of a live tick (1 stream x 1 frame: 19.7 -> ~8 us of kernel time)
+    *warps_per_cta = std::max(std::min(8, max_wpc), std::min(max_wpc, per_cta));
 }
 
 template<int MAXW, bool TSM, bool GATE, bool EXTRA>
