@@ -140,7 +140,8 @@ typedef struct wf_batch {
     const float *pcm;          /* planar float PCM, host or device */
     int64_t stream_stride;     /* in floats */
     int64_t channel_stride;    /* in floats */
-    const float *input_rms;    /* optional [n_streams][n_frames] m_input_rms per tick (volume normalisation) */
+    const float *input_rms;    /* [n_streams][n_frames] m_input_rms per tick; REQUIRED when normalize_volume is set (else
+                                  WF_ERR_INVALID_ARG: never a silent max_gain), ignored otherwise */
     const uint8_t *skip_mask;  /* optional [n_streams][n_frames]: nonzero = "not enough audio" for that tick */
     float *out_db;             /* optional [n_streams][n_frames][display_channels][bins]       m_decibels      */
     float *out_points;         /* optional [n_streams][n_frames][display_channels][num_points] interpolated dB */

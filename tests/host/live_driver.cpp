@@ -1,5 +1,5 @@
 // live_driver: feeds packets / ticks to wfhost::SpectrumSourceCUDA the way OBS would and dumps m_decibels per tick.
-// usage: live_driver <pcm.f32> <channels> <samples_per_channel> <fft_size> <packet> <fps> <ticks> <out.f32> [stereo]
+// usage: live_driver <pcm.f32> <channels> <samples_per_channel> <fft_size> <packet> <fps> <ticks> <out.f32> [stereo] [normalize_volume]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -16,6 +16,7 @@ int main(int argc, char **argv)
     const int N = atoi(argv[4]), packet = atoi(argv[5]), fps = atoi(argv[6]), ticks = atoi(argv[7]);
     const char *out = argv[8];
     const bool stereo = argc > 9 && atoi(argv[9]) != 0;
+    const bool normalize = argc > 10 && atoi(argv[10]) != 0;
     std::vector<float> pcm((size_t)cc * ns);
     FILE *f = fopen(in, "rb");
     if(!f || fread(pcm.data(), sizeof(float), pcm.size(), f) != pcm.size())
@@ -27,6 +28,7 @@ int main(int argc, char **argv)
     cfg.fft_size = N;
     cfg.capture_channels = cc;
     cfg.stereo = stereo;
+    cfg.normalize_volume = normalize;
     wfhost::SpectrumSourceCUDA src;
     uint64_t now = 10ull * 1000000000ull;
     int rc = src.update(cfg, 0, now);

@@ -55,8 +55,8 @@ def _reference_live(settings, cc, pcm, N, packet, fps, ticks):
     return np.stack(out), np.array(sil, dtype=np.uint8)
 
 
-@pytest.mark.parametrize("N,cc,stereo", [(4096, 2, 1), (2048, 1, 0), (1024, 2, 0)])
-def test_live_adapter_matches_reference_plugin(tmp_path, N, cc, stereo):
+@pytest.mark.parametrize("N,cc,stereo,normalize", [(4096, 2, 1, 0), (2048, 1, 0, 0), (1024, 2, 0, 0), (2048, 2, 1, 1), (800, 1, 0, 1)])
+def test_live_adapter_matches_reference_plugin(tmp_path, N, cc, stereo, normalize):
     exe = _build_driver(tmp_path)
     packet, fps, ticks = 480, 60, 45
     ns = 48000
@@ -65,7 +65,7 @@ def test_live_adapter_matches_reference_plugin(tmp_path, N, cc, stereo):
     inp, outp = tmp_path / "pcm.f32", tmp_path / "out.f32"
     pcm.astype(np.float32).tofile(inp)
     r = subprocess.run([str(exe), str(inp), str(cc), str(ns), str(N), str(packet), str(fps), str(ticks), str(outp),
-                        str(stereo)], capture_output=True, text=True)
+                        str(stereo), str(normalize)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     B = N // 2
     dch = 2 if stereo else 1
@@ -73,6 +73,8 @@ def test_live_adapter_matches_reference_plugin(tmp_path, N, cc, stereo):
     got = raw[:, :-1].copy().view(np.float32).reshape(ticks, dch, B)
     got_sil = raw[:, -1]
     settings = {"fft_size": N, "channel_mode": "stereo" if stereo else "mono"}
+    if normalize:  # the RMS feed runs live in both: capture_audio pre-accumulate + update_input_rms (not forced)
+        settings["normalize_volume"] = True
     ref, ref_sil = _reference_live(settings, cc, pcm, N, packet, fps, ticks)
     assert np.array_equal(got_sil, ref_sil)
     rep = parity_report(got, ref)

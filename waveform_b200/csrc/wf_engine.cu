@@ -934,6 +934,9 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         return set_err(e, WF_ERR_INVALID_ARG, "pcm is null");
     if(b->stream_stride < 0 || b->channel_stride < 0)
         return set_err(e, WF_ERR_INVALID_ARG, "negative strides are not supported");
+    if(t.cfg.normalize_volume && !b->input_rms)
+        return set_err(e, WF_ERR_INVALID_ARG, "normalize_volume is set but the batch carries no input_rms (m_input_rms per tick: "
+                                              "wf_meter in WF_METER_INPUT_RMS mode, or the host's own update_input_rms)");
     if((b->out_points || b->out_pixels || b->out_min) && t.num_points <= 0)
         return set_err(e, WF_ERR_INVALID_ARG, "display outputs requested but the engine has no display points");
 

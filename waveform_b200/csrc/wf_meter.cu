@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -289,6 +290,111 @@ __global__ void meter_scan_kernel(const MParams p)
     p.flags[s] = last_silent ? 1 : 0;
 }
 
+// ---- one-pass path: hop divides the window (the plugin's usual case: 150 ms at 48 kHz = 7200 = 9 x 800 samples at 60 fps) ----
+// One CTA per stream.  Every hop-sized block of the stream's timeline (W/hop blocks of history ring, then one block per
+// tick) is reduced ONCE by one warp with 128-bit loads — the same pass copies the last W samples into the next call's ring —
+// and its partial lands in shared memory; a tick's window is then exactly W/hop consecutive partials, combined by one
+// thread per (tick, channel); finally the per-stream recurrence (EMA, dBFS, m_last_silent) runs on one lane per channel.
+// Samples cross HBM once, nothing else does: the three-kernel path above wrote and re-read per-32-sample partials W/hop times.
+template<int MODE>
+__global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
+{
+    extern __shared__ float sm[];
+    const int T = p.n_ticks, hop = p.hop, W = p.W, pc = p.pc, cc = p.cc;
+    const int nb = W / hop, NB = nb + T;
+    float *part = sm;                 // [pc][NB]
+    float *raw = sm + (size_t)pc * NB; // [T][pc]
+    const int s = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool two = (MODE == WF_METER_INPUT_RMS) && cc > 1;
+    const int q4 = hop >> 2;
+    for(int w = warp; w < pc * NB; w += nwarps)
+    {
+        const int c = w / NB, b = w - c * NB;
+        const Row r0 = row_of(p, s, c);
+        const Row r1 = two ? row_of(p, s, 1) : r0;
+        const float4 *src0 = reinterpret_cast<const float4 *>((b < nb) ? r0.hist + (size_t)b * hop : r0.pcm + (size_t)(b - nb) * hop);
+        const float4 *src1 = reinterpret_cast<const float4 *>((b < nb) ? r1.hist + (size_t)b * hop : r1.pcm + (size_t)(b - nb) * hop);
+        const bool keep = b >= T; // one of the last W/hop blocks: belongs to the next call's ring
+        float4 *h0 = reinterpret_cast<float4 *>(p.hist_next + ((size_t)s * cc + c) * W + (size_t)(b - T) * hop);
+        float4 *h1 = reinterpret_cast<float4 *>(p.hist_next + ((size_t)s * cc + 1) * W + (size_t)(b - T) * hop);
+        float acc = 0.0f;
+        for(int i = lane; i < q4; i += 32)
+        {
+            const float4 a = (b < nb) ? src0[i] : __ldg(src0 + i);
+            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if(two)
+                a1 = (b < nb) ? src1[i] : __ldg(src1 + i);
+            acc = combine<MODE>(acc, combine<MODE>(combine<MODE>(contrib<MODE>(a.x, a1.x), contrib<MODE>(a.y, a1.y)),
+                                                   combine<MODE>(contrib<MODE>(a.z, a1.z), contrib<MODE>(a.w, a1.w))));
+            if(keep)
+            {
+                h0[i] = a;
+                if(two)
+                    h1[i] = a1;
+            }
+        }
+        acc = warp_combine<MODE>(acc);
+        if(lane == 0)
+            part[c * NB + b] = acc;
+    }
+    __syncthreads();
+    // window of tick t = blocks [t+1, t+1+nb)
+    for(int idx = threadIdx.x; idx < T * pc; idx += blockDim.x)
+    {
+        const int t = idx / pc, c = idx - t * pc;
+        const float *q = part + c * NB + t + 1;
+        float acc = q[0];
+        for(int i = 1; i < nb; ++i)
+            acc = combine<MODE>(acc, q[i]);
+        raw[idx] = acc;
+    }
+    __syncthreads();
+    if(MODE == WF_METER_INPUT_RMS)
+    {
+        for(int t = threadIdx.x; t < T; t += blockDim.x)
+            if(p.out_lin)
+                p.out_lin[(size_t)s * T + t] = __fsqrt_rn(__fdiv_rn(raw[t], (float)W)); // src/source_generic.cpp:402
+        return;
+    }
+    if(warp == 0)
+    {
+        // per-stream recurrence (src/source_generic.cpp:232-269): lane c < cc walks its channel, the silent rule needs both
+        const int c = (lane < cc) ? lane : 0;
+        float buf = p.buf[2 * s + c];
+        bool last_silent = p.flags[s] != 0;
+        for(int t = 0; t < T; ++t)
+        {
+            float out = raw[t * pc + c];
+            if(MODE == WF_METER_RMS)
+                out = __fsqrt_rn(__fdiv_rn(out, (float)W)); // :243
+            if(p.tsmooth)
+            {
+                if(!p.fast_peaks || (out <= buf))
+                    out = __fadd_rn(__fmul_rn(p.g, buf), __fmul_rn(p.g2, out)); // :255-256
+            }
+            buf = out;
+            const float val = (out > 0.0f) ? 20.0f * log10f(out) : p.db_min; // dbfs, src/source.hpp:293-299
+            const unsigned below = __ballot_sync(0xffffffffu, (lane < cc) && (val < p.floor_m10));
+            last_silent = __popc(below) >= cc; // :264-269
+            if(lane < cc)
+            {
+                const size_t o = ((size_t)s * T + t) * cc + c;
+                if(p.out_db)
+                    p.out_db[o] = val;
+                if(p.out_lin)
+                    p.out_lin[o] = out;
+            }
+            if(p.out_silent && lane == 0)
+                p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
+        }
+        if(lane < cc)
+            p.buf[2 * s + c] = buf;
+        if(lane == 0)
+            p.flags[s] = last_silent ? 1 : 0;
+    }
+}
+
 __global__ void meter_fill_kernel(float *q, long long n, float v)
 {
     for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -328,6 +434,7 @@ struct wf_meter {
     int64_t launches = 0;
     float *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
+    bool use_fused = true; // WF_METER_FUSED=0: always the three-kernel path (A/B tests)
     float *d_buf = nullptr;
     unsigned char *d_flags = nullptr;
     // scratch / staging
@@ -467,6 +574,10 @@ int wf_meter_create(const wf_meter_config *cfg, wf_meter **out)
             return bail(merr(m, (_err == cudaErrorMemoryAllocation) ? WF_ERR_OOM : WF_ERR_CUDA, "%s: %s", #call, \
                              cudaGetErrorString(_err)));                                             \
     } while(0)
+    {
+        const char *mf = getenv("WF_METER_FUSED");
+        m->use_fused = !(mf && mf[0] == '0');
+    }
     WFM_C(cudaSetDevice(dev));
     cudaDeviceProp prop{};
     WFM_C(cudaGetDeviceProperties(&prop, dev));
@@ -635,6 +746,33 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     constexpr int kWarps = 8;
     // 128-bit loads need 16-byte aligned rows (W is a multiple of 16 samples already)
     const int vec4 = (((uintptr_t)d_pcm & 15u) == 0) && ((b->stream_stride & 3) == 0) && ((b->channel_stride & 3) == 0);
+    // one-pass path: the window is a whole number of hops (meter_fused_kernel)
+    const size_t fused_smem = ((size_t)pc * ((size_t)(W / b->hop) + T) + T * pc) * sizeof(float);
+    const bool fused = m->use_fused && vec4 && (W % b->hop) == 0 && (b->hop % 4) == 0 && fused_smem <= 96 * 1024;
+    if(fused)
+    {
+        p.bl = b->hop;
+        p.nblk = (int)(W / b->hop + T);
+        auto launch = [&](auto kernel) -> cudaError_t {
+            if(fused_smem > 48 * 1024)
+            {
+                cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                if(err != cudaSuccess)
+                    return err;
+            }
+            kernel<<<(int)S, 256, fused_smem, st>>>(p);
+            return cudaGetLastError();
+        };
+        switch(m->cfg.mode)
+        {
+        case WF_METER_PEAK: WFM_CUDA(m, launch(meter_fused_kernel<WF_METER_PEAK>)); break;
+        case WF_METER_RMS: WFM_CUDA(m, launch(meter_fused_kernel<WF_METER_RMS>)); break;
+        default: WFM_CUDA(m, launch(meter_fused_kernel<WF_METER_INPUT_RMS>)); break;
+        }
+        m->launches += 1;
+    }
+    else
+    {
     const int g1 = grid_for((long long)S * pc * nchunk, kWarps, m->sm_count), g2 = grid_for((long long)S * T * pc, kWarps, m->sm_count);
     switch(m->cfg.mode)
     {
@@ -655,6 +793,7 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     meter_scan_kernel<<<(int)((S + 127) / 128), 128, 0, st>>>(p);
     WFM_CUDA(m, cudaGetLastError());
     m->launches += 3;
+    }
     WFM_CUDA(m, cudaEventRecord(m->ev1, st));
     m->ev_valid = true;
     // The ring is double-buffered per ENGINE, so a call must cover every stream whose history should survive: copy the

@@ -2,6 +2,7 @@
 #include "spectrum_source.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace wfhost {
@@ -29,6 +30,8 @@ void RingBuffer::reserve(size_t bytes)
 }
 void RingBuffer::push_back(const void *data, size_t bytes)
 {
+    if(bytes == 0) // nothing to do — and no modulo by an empty buffer's size (the reference guards size == 0 too,
+        return;    // src/circular_buffer.hpp:46,70)
     reserve(m_size + bytes);
     const size_t tail = (m_head + m_size) % m_buf.size();
     const size_t first = std::min(bytes, m_buf.size() - tail);
@@ -38,6 +41,8 @@ void RingBuffer::push_back(const void *data, size_t bytes)
 }
 void RingBuffer::push_back_zero(size_t bytes)
 {
+    if(bytes == 0)
+        return;
     reserve(m_size + bytes);
     const size_t tail = (m_head + m_size) % m_buf.size();
     const size_t first = std::min(bytes, m_buf.size() - tail);
@@ -47,6 +52,8 @@ void RingBuffer::push_back_zero(size_t bytes)
 }
 void RingBuffer::peek_front(void *dst, size_t bytes) const
 {
+    if(bytes == 0 || m_buf.empty())
+        return;
     const size_t first = std::min(bytes, m_buf.size() - m_head);
     memcpy(dst, m_buf.data() + m_head, first);
     memcpy((uint8_t *)dst + first, m_buf.data(), bytes - first);
@@ -106,6 +113,13 @@ int SpectrumSourceCUDA::update(const wf_config &cfg, int64_t ts_offset_ns, uint6
     for(int c = 0; c < 2; ++c)
         m_decibels[c].assign((size_t)m_info.bins, m_info.db_min); // src/source.cpp:1181
     m_last_silent = false;
+    // volume normalisation feed, src/source.cpp:1145-1152
+    m_rms_sync.reset();
+    m_rms_ring.clear();
+    m_rms_pos = 0;
+    m_input_rms = 0.0f;
+    if(m_cfg.normalize_volume)
+        m_rms_ring.assign((size_t)(m_cfg.sample_rate & ~15u), 0.0f);
     m_capture_ts = now_ns; // src/source.cpp:1242
     // pre-fill with silence to avoid start-up lag, src/source.cpp:1243-1248
     for(int c = 0; c < m_info.capture_channels; ++c)
@@ -122,7 +136,7 @@ int64_t SpectrumSourceCUDA::audio_sync(uint64_t ts) const
     return (audio_ts < ts) ? -(int64_t)delta : (int64_t)delta;
 }
 
-// capture_audio, src/source.cpp:1817-1888 (without the RMS feed, which belongs to volume normalisation's caller)
+// capture_audio, src/source.cpp:1817-1888
 void SpectrumSourceCUDA::capture_audio(const float *const *data, uint32_t frames, uint64_t timestamp_ns, uint64_t now_ns,
                                        bool muted)
 {
@@ -136,6 +150,23 @@ void SpectrumSourceCUDA::capture_audio(const float *const *data, uint32_t frames
     const size_t bufsz = (size_t)m_info.fft_size * sizeof(float);
     const int64_t dtaudio = audio_sync(m_capture_ts);
     const size_t dtsamples = (dtaudio > 0) ? (size_t)ns_to_frames(sr, (uint64_t)dtaudio) : 0;
+    // RMS pre-accumulate: one value per time point, the square of the LARGEST channel (src/source.cpp:1842-1871)
+    if(m_cfg.normalize_volume)
+    {
+        m_rms_tmp.resize(frames);
+        for(uint32_t i = 0; i < frames; ++i)
+        {
+            float val = 0.0f;
+            for(int j = 0; j < m_info.capture_channels; ++j)
+                if(data[j] != nullptr)
+                    val = std::max(std::abs(data[j][i]), val);
+            m_rms_tmp[i] = val * val;
+        }
+        m_rms_sync.push_back(m_rms_tmp.data(), (size_t)frames * sizeof(float));
+        const size_t max_rms = (dtsamples + m_rms_ring.size()) * sizeof(float);
+        if(m_rms_sync.size() > max_rms)
+            m_rms_sync.pop_front(nullptr, m_rms_sync.size() - max_rms);
+    }
     const size_t sz = (size_t)frames * sizeof(float);
     for(int j = 0; j < m_info.capture_channels; ++j)
     {
@@ -150,12 +181,45 @@ void SpectrumSourceCUDA::capture_audio(const float *const *data, uint32_t frames
     }
 }
 
+// sync_rms_buffer (src/source.cpp:810-836) + update_input_rms (src/source_generic.cpp:392-403): move the values that are
+// due (everything but the A/V-sync delay) into the one-second ring, then sqrt(mean) with ONE float accumulator in ring-index
+// order (the reference's rounding; the order is not time order once the ring has wrapped).
+void SpectrumSourceCUDA::update_input_rms()
+{
+    const int64_t dtaudio = audio_sync(m_tick_ts);
+    const size_t dtsize = (dtaudio > 0) ? (size_t)ns_to_frames(m_cfg.sample_rate, (uint64_t)dtaudio) * sizeof(float) : 0;
+    if(m_rms_sync.size() <= dtsize)
+        return;
+    const size_t n = m_rms_ring.size();
+    while(m_rms_sync.size() > dtsize)
+    {
+        const size_t consume = m_rms_sync.size() - dtsize;
+        const size_t room = (n - m_rms_pos) * sizeof(float);
+        if(consume >= room)
+        {
+            m_rms_sync.pop_front(&m_rms_ring[m_rms_pos], room);
+            m_rms_pos = 0;
+        }
+        else
+        {
+            m_rms_sync.pop_front(&m_rms_ring[m_rms_pos], consume);
+            m_rms_pos += consume / sizeof(float);
+        }
+    }
+    float sum = 0.0f;
+    for(size_t i = 0; i < n; ++i)
+        sum += m_rms_ring[i];
+    m_input_rms = std::sqrt(sum / n);
+}
+
 // tick (src/source.cpp:1324-1344) + the host half of tick_spectrum (src/source_generic.cpp:26-61)
 int SpectrumSourceCUDA::tick(float seconds, uint64_t now_ns)
 {
     if(!m_engine || m_info.capture_channels == 0)
         return WF_OK;
     m_tick_ts = now_ns;
+    if(m_cfg.normalize_volume)
+        update_input_rms(); // src/source.cpp:1330-1331
     const size_t N = (size_t)m_info.fft_size, B = (size_t)m_info.bins;
     const size_t bufsz = N * sizeof(float);
 
@@ -200,6 +264,7 @@ int SpectrumSourceCUDA::tick(float seconds, uint64_t now_ns)
     b.stream_stride = (int64_t)(m_info.capture_channels * N);
     b.channel_stride = (int64_t)N;
     b.skip_mask = &skip;
+    b.input_rms = m_cfg.normalize_volume ? &m_input_rms : nullptr;
     b.out_db = m_out.data();
     uint8_t silent = 0;
     b.out_silent = &silent;

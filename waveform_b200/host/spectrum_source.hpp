@@ -10,6 +10,8 @@
 //   SpectrumSourceCUDA::capture_audio ≙ WAVSource::capture_audio  src/source.cpp:1817-1888
 //   SpectrumSourceCUDA::tick       ≙ WAVSource::tick + tick_spectrum src/source.cpp:1324-1344, src/source_generic.cpp:26-61
 //   audio_sync                     ≙ WAVSource::get_audio_sync    src/source.hpp:279-285
+//   update_input_rms               ≙ sync_rms_buffer + WAVSourceGeneric::update_input_rms  src/source.cpp:810-836,
+//                                    src/source_generic.cpp:392-403 (the RMS pre-accumulate of capture_audio: src/source.cpp:1842-1871)
 // Threading is the caller's, as in the plugin (m_mtx around tick/render/update; capture_audio try-locks).
 #pragma once
 #include <cstdint>
@@ -57,6 +59,7 @@ public:
     void hide() { m_show = false; }
     const float *decibels(int display_channel) const { return m_decibels[display_channel].data(); }
     bool last_silent() const { return m_last_silent; }
+    float input_rms() const { return m_input_rms; } // m_input_rms: RMS over the last second, volume normalisation's input
     int bins() const { return m_info.bins; }
     int display_channels() const { return m_info.display_channels; }
     const wf_info &info() const { return m_info; }
@@ -64,6 +67,7 @@ public:
 
 private:
     int64_t audio_sync(uint64_t ts) const;
+    void update_input_rms();
     wf_engine *m_engine = nullptr;
     wf_config m_cfg{};
     wf_info m_info{};
@@ -74,6 +78,12 @@ private:
     bool m_show = true, m_last_silent = false;
     uint64_t m_capture_ts = 0, m_audio_ts = 0, m_tick_ts = 0;
     int64_t m_ts_offset = 0;
+    // volume normalisation feed (≙ m_rms_sync_buf / m_input_rms_buf / m_input_rms, src/source.hpp:238-244): per captured
+    // sample (max over channels |x|)^2, A/V-synchronised, RMS over the last sample_rate & -16 values
+    RingBuffer m_rms_sync;
+    std::vector<float> m_rms_ring, m_rms_tmp;
+    size_t m_rms_pos = 0;
+    float m_input_rms = 0.0f;
 };
 
 } // namespace wfhost
