@@ -319,19 +319,38 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
         float4 *h0 = reinterpret_cast<float4 *>(p.hist_next + ((size_t)s * cc + c) * W + (size_t)(b - T) * hop);
         float4 *h1 = reinterpret_cast<float4 *>(p.hist_next + ((size_t)s * cc + 1) * W + (size_t)(b - T) * hop);
         float acc = 0.0f;
-        for(int i = lane; i < q4; i += 32)
+        // four 128-bit loads in flight per lane and channel (a hop of 800 samples is 6.25 loads per lane)
+        for(int i0 = lane; i0 < q4; i0 += 128)
         {
-            const float4 a = (b < nb) ? src0[i] : __ldg(src0 + i);
-            float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if(two)
-                a1 = (b < nb) ? src1[i] : __ldg(src1 + i);
-            acc = combine<MODE>(acc, combine<MODE>(combine<MODE>(contrib<MODE>(a.x, a1.x), contrib<MODE>(a.y, a1.y)),
-                                                   combine<MODE>(contrib<MODE>(a.z, a1.z), contrib<MODE>(a.w, a1.w))));
-            if(keep)
+            float4 a[4], a1[4];
+#pragma unroll
+            for(int u = 0; u < 4; ++u)
             {
-                h0[i] = a;
-                if(two)
-                    h1[i] = a1;
+                const int i = i0 + 32 * u;
+                a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                a1[u] = a[u];
+                if(i < q4)
+                {
+                    a[u] = (b < nb) ? src0[i] : __ldg(src0 + i);
+                    if(two)
+                        a1[u] = (b < nb) ? src1[i] : __ldg(src1 + i);
+                }
+            }
+#pragma unroll
+            for(int u = 0; u < 4; ++u)
+            {
+                const int i = i0 + 32 * u;
+                if(i < q4) // (zeros would be neutral for all three modes, but the ring must only take real samples)
+                {
+                    acc = combine<MODE>(acc, combine<MODE>(combine<MODE>(contrib<MODE>(a[u].x, a1[u].x), contrib<MODE>(a[u].y, a1[u].y)),
+                                                           combine<MODE>(contrib<MODE>(a[u].z, a1[u].z), contrib<MODE>(a[u].w, a1[u].w))));
+                    if(keep)
+                    {
+                        h0[i] = a[u];
+                        if(two)
+                            h1[i] = a1[u];
+                    }
+                }
             }
         }
         acc = warp_combine<MODE>(acc);
