@@ -12,7 +12,8 @@ and outputs (256 MiB) are each larger than the 126 MB L2, so every step streams 
 Besides the contract's keys the line carries:
   parity            the measured launch (same engine geometry, fresh state) against the reference's generic CPU path on a
                     sample of streams: SURVEY.md §8(d) "first 256 frames/shard" + streams from the far ends of the grid
-  config.extra      the other layouts of the same 65 536-frame batch (65536x1 ... 256x256) with their roofline fractions,
+  config.extra      the other layouts of the same 65 536-frame batch (65536x1 ... 256x256) with their roofline fractions, the
+                    other BASELINE.json configs / kernel families (other_shapes: N=4096, 8192, 800, 1920, c1, c2, c4, c5),
                     a strong-scaling number (65 536 frames TOTAL over the N GPUs) and BASELINE.json configs[4]
                     (N=16384, 128 streams x 256 ticks per GPU, NCCL MAX all-reduce + normalise pass inside the timed loop)
   cpu_baseline      all-cores AVX2 (the value) plus AVX2 on one core and the generic path on one core
@@ -519,9 +520,12 @@ def run_gpu_arm(args):
         traffic, traffic_src = load_traffic() if (S, T) == (4096, 16) else (None, None)
         kernel_ms = statistics.mean(per_launch)
         achieved = frames_per_gpu * BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
-        layouts = None
+        layouts, other = None, None
         if world == 1 and not args.no_layouts:
             layouts = run_layouts(torch, device, stream, peak_gbs, steps=20)
+            sys.path.insert(0, str(ROOT / "tools"))
+            from bench_shapes import run_shapes
+            other = run_shapes(torch, iters=5, peak_gbs=peak_gbs)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, ALL_CPUS)  # the CPU arm uses every core the box grants, not just the GPU's NUMA node
@@ -544,7 +548,7 @@ def run_gpu_arm(args):
                        "hop": N_FFT, "frames_per_step_per_gpu": frames_per_gpu,
                        "l2_policy": "inputs 512 MiB + outputs 256 MiB per step exceed the 126 MB L2 (no flush needed)",
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                       "extra": {"layouts_same_batch": layouts, "strong_scaling": strong, "c5": c5}},
+                       "extra": {"layouts_same_batch": layouts, "strong_scaling": strong, "c5": c5, "other_shapes": other}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(S * T * N_FFT * 4),
                     "d2h_bytes_per_step": int(S * T * BINS * 4), "steps": e2e_steps, "checksum": checksum,

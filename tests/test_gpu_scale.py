@@ -375,53 +375,3 @@ def test_per_tick_seconds_tv_exponential(N, S, team_w, monkeypatch):
             o.tick([pcm[s, 0, t * N:(t + 1) * N]], float(secs[t]))
             rep = parity_report(out["db"][s, t], np.stack([o.decibels(0)]), db_min=eng.db_min)
             assert rep["ok"] and rep["normwise"] < 1e-6, (eng.last_kernel_name(), s, t, rep)
-
-
-@pytest.mark.parametrize("variant", ["plain", "options"])
-def test_pair4096_two_warps_per_stream(variant, monkeypatch):
-    """wf_pair4096.cuh (N = 4096, the plugin's default size: a radix-2 split across two warps, each running the N=2048
-    kernel's FFT): parity against the oracle incl. the gate's freeze / wake-up across a call boundary, skip mask, per-tick
-    gravity and the option set; agreement with the CTA-per-tick kernel it replaces."""
-    import torch
-    from waveform_b200 import Engine
-
-    N = 4096
-    if variant == "plain":
-        settings = {"fft_size": N, "window": "hann", "gravity": 0.3, "floor": -40}
-    else:
-        settings = {"fft_size": N, "window": "blackman_harris", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0, "fast_peaks": True,
-                    "temporal_smoothing": "tv_exp_moving_avg", "gravity": 0.5, "normalize_volume": True}
-    S, T = 41, 28
-    pcm = synth_pcm(S, 1, T * N, zero_frames=[(1, 3, 7), (2, 0, 28), (5, 4, 28), (9, 27, 28)], frame_len=N, hop=N)
-    pcm[5, :, 20 * N: 21 * N] = 0.1
-    rng = np.random.default_rng(4)
-    rms = (0.02 + 0.3 * rng.uniform(size=(S, T))).astype(np.float32) if variant == "options" else None
-    secs = (1.0 / 60.0 * (0.5 + rng.uniform(size=T))).astype(np.float32) if variant == "options" else None
-    x = torch.from_numpy(pcm).cuda()
-    outs = {}
-    for name, thr in (("pair", "1"), ("v3", "1000000000")):
-        monkeypatch.setenv("WF_PAIR_MIN_STREAMS", thr)
-        eng = Engine(settings, channels=1, max_streams=S)
-        kw1 = dict(input_rms=None if rms is None else torch.from_numpy(rms[:, :11].copy()).cuda(),
-                   frame_seconds=None if secs is None else secs[:11], want_peak=True)
-        kw2 = dict(input_rms=None if rms is None else torch.from_numpy(rms[:, 11:].copy()).cuda(),
-                   frame_seconds=None if secs is None else secs[11:], want_peak=True)
-        a = eng.process(x[:, :, : 11 * N].contiguous(), 11, N, **kw1)
-        b = eng.process(x[:, :, 11 * N:].contiguous(), T - 11, N, **kw2)
-        torch.cuda.synchronize()
-        want = "stft4096_pair_kernel" if name == "pair" else "stft_v3_kernel<4096"
-        assert eng.last_kernel_name().startswith(want), eng.last_kernel_name()
-        outs[name] = ({k: torch.cat([a[k], b[k]], dim=1 if k != "peak" else 0).cpu().numpy() for k in ("db", "silent", "peak")},
-                      eng.get_state())
-    got, st = outs["pair"]
-    assert np.array_equal(got["silent"], outs["v3"][0]["silent"])
-    rep = parity_report(got["db"], outs["v3"][0]["db"], db_min=-758.0)
-    assert rep["ok"], rep
-    assert np.allclose(got["peak"], outs["v3"][0]["peak"], atol=2e-3)
-    assert np.array_equal(st["flags"], outs["v3"][1]["flags"])
-    if variant == "plain":
-        ref_db, _, ref_sil = _oracle_rows(settings, 1, pcm, T, N)
-        assert np.array_equal(got["silent"], ref_sil) and ref_sil.sum() > 10
-        rep = parity_report(got["db"], ref_db, db_min=-758.0)
-        assert rep["ok"] and rep["normwise"] < 1e-6, rep
-        assert parity_report(st["hold_db"][:, 0], ref_db[:, -1, 0], db_min=-758.0)["ok"]   # m_decibels mirror after the call

@@ -24,7 +24,6 @@
 #include "wf_v3.hpp"
 #include "wf_team2048.hpp"
 #include "wf_warp2.hpp"
-#include "wf_pair4096.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -52,8 +51,6 @@ struct wf_engine {
     // device tables
     float *d_window = nullptr, *d_slope = nullptr, *d_rolloff = nullptr;
     float *d_tw = nullptr, *d_tw_post = nullptr;
-    float *d_tw_h = nullptr, *d_window_s = nullptr; // N = 4096 pair kernel: W_1024^k and the window scaled by (2/sum(w))/2
-    int pair_min_streams = 296;                     // WF_PAIR_MIN_STREAMS: fewer streams stay on the CTA-per-tick kernel (0 disables the pair kernel: 1<<30)
     float *d_tw1 = nullptr, *d_tw2 = nullptr, *d_tw0 = nullptr; // inter-pass twiddles of the CTA-per-tick kernel (wf_v3.cuh), N = 4096/8192/16384
     // N=2048: the warp-per-stream kernel needs ~2400 streams to fill the GPU; with fewer streams AND long per-stream tick
     // sequences (>= 32) the cluster kernel (wf_v3.cuh, up to 8 ticks of a stream in flight) is faster: measured 256x256
@@ -583,9 +580,6 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->team_w = atoi(tw);
         const char *zc = getenv("WF_ZERO_COPY");
         e->zero_copy = !(zc && zc[0] == '0');
-        const char *pm = getenv("WF_PAIR_MIN_STREAMS");
-        if(pm)
-            e->pair_min_streams = atoi(pm);
         const char *w2 = getenv("WF_WARP2");
         e->use_warp2 = !(w2 && w2[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
@@ -636,22 +630,6 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         WF_TRY(upload(e, &e->d_tw2, tw2));
         WF_TRY(upload(e, &e->d_tw0, tw0));
     }
-    if(t.N == 4096)
-    {
-        const int H = t.N / 4;
-        std::vector<float> twh((size_t)2 * H), ws((size_t)t.N);
-        for(int k = 0; k < H; ++k)
-        {
-            const double a = -2.0 * 3.14159265358979323846264338327950288 * (double)k / (double)H;
-            twh[2 * k] = (float)std::cos(a);
-            twh[2 * k + 1] = (float)std::sin(a);
-        }
-        const float ch = (2.0f / t.window_sum) * 0.5f;
-        for(int i = 0; i < t.N; ++i)
-            ws[i] = (t.window.empty() ? 1.0f : t.window[i]) * ch;
-        WF_TRY(upload(e, &e->d_tw_h, twh));
-        WF_TRY(upload(e, &e->d_window_s, ws));
-    }
     WF_TRY(upload(e, &e->d_interp_idx, t.interp_indices));
     WF_TRY(upload(e, &e->d_interp_w, t.interp_weights));
     WF_TRY(upload(e, &e->d_gauss, t.gauss));
@@ -679,7 +657,7 @@ void wf_destroy(wf_engine *e)
         cudaSetDevice(e->device);
         cudaStreamSynchronize(e->stream);
     }
-    void *ptrs[] = {e->d_tw_h, e->d_window_s, e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_tw0, e->d_interp_idx, e->d_interp_w,
+    void *ptrs[] = {e->d_window, e->d_slope, e->d_rolloff, e->d_tw, e->d_tw_post, e->d_tw1, e->d_tw2, e->d_tw0, e->d_interp_idx, e->d_interp_w,
                     e->d_gauss, e->d_band_widths, e->d_band_offsets, e->d_state, e->d_hold, e->d_flags, e->s_pcm,
                     e->s_out_db, e->s_out_points, e->s_rms, e->s_peak, e->s_skip, e->s_silent, e->s_scratch, e->s_px, e->s_min, e->s_gtab};
     for(void *p : ptrs)
@@ -812,8 +790,6 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     kp.window2 = reinterpret_cast<const float2 *>(e->d_window);
     kp.tw = reinterpret_cast<const float2 *>(e->d_tw);
     kp.tw_post = reinterpret_cast<const float2 *>(e->d_tw_post);
-    kp.tw_h = reinterpret_cast<const float2 *>(e->d_tw_h);
-    kp.window2s = reinterpret_cast<const float2 *>(e->d_window_s);
     kp.slope = e->d_slope;
     kp.rolloff = e->d_rolloff;
     const size_t slot = (size_t)b->first_stream + (size_t)s0;
@@ -922,21 +898,6 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         const int rc = materialize_hold(e, st); // the other kernels read hold_db as it is
         if(rc)
             return rc;
-    }
-    // N = 4096, the plugin's default size: two warps per stream (wf_pair4096.cuh) when the streams fill the SMs' pairs
-    const bool pair_ok = (N == 4096) && e->d_tw_h && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points && !kp.out_pixels &&
-                         !kp.out_min && aligned16 && !e->force_generic && kp.n_streams >= e->pair_min_streams;
-    if(pair_ok)
-    {
-        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
-        kp.lazy_hold = e->lazy_hold ? 1 : 0;
-        if(kp.lazy_hold)
-            e->hold_implicit = true;
-        const int grid = std::min(e->sm_count, kp.n_streams);
-        WF_CUDA(e, pair4096_launch(x, kp, grid, st, e->use_pdl, e->device));
-        e->launches++;
-        e->last_kernel = "stft4096_pair_kernel<" + std::to_string((int)x) + "> grid " + std::to_string(grid) + " x 8 pairs";
-        return WF_OK;
     }
     // Non-power-of-two sizes with a compiled two-pass plan (wf_warp2.cuh): same launch shape as the N=2048 kernel.
     const bool warp2_ok = e->use_warp2 && warp2_supported(N) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points &&

@@ -34,8 +34,6 @@ struct KParams {
     const float *window;   // same table, scalar view
     const float2 *tw;      // W_M^k
     const float2 *tw_post; // W_N^k, k < M
-    const float2 *tw_h;    // W_(M/2)^k, k < M/2 (N = 4096 pair kernel: twiddles of the two half-size sub-FFTs) or null
-    const float2 *window2s;// window pairs x (2/sum(w))/2 in global memory (N = 4096 pair kernel; all-equal without a window) or null
     const float *slope;    // or null
     const float *rolloff;  // or null
     // per-stream persistent state (already offset by first_stream)
