@@ -424,16 +424,17 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             ema_g2 = gt.y;
         }
     };
-    auto ema = [&](float mag, float &state, bool do_proc) {
+    auto ema = [&](float mag, float &state) {
         float oldval = state;
         if(XF && p.fast_peaks)
             oldval = fmaxf(mag, oldval);
-        mag = __fadd_rn(__fmul_rn(ema_g, oldval), __fmul_rn(ema_g2, mag));
-        if(do_proc)
-            state = mag;
+        state = __fadd_rn(__fmul_rn(ema_g, oldval), __fmul_rn(ema_g2, mag));
     };
     // split pass of pair j of my tick -> (|X[k1]|, |X[k2]|), normalised, slope applied (src/source_generic.cpp:110-122)
     auto split_pair = [&](const pk::c64 *X, const pk::c64 *twp, int j, float &m1, float &m2) {
+        // |X| through MUFU.SQRT in its flush-to-zero form, as wf_fast2048.cuh: the subnormal-safe variant costs an FSETP and two
+        // FMULs per bin (ncu, profiles/r01k_v3_8192.txt: 776 FMUL + 520 FSETP per N=8192 frame); powers below FLT_MIN
+        // (|X| < 1e-19, -380 dBFS — digital silence) become exact zeros, which dbfs reports as DB_MIN.
         const int k1 = tid + j * TN;
         const pk::c64 a = X[k1];
         // X[M - k1]: descending addresses (conflict free); thread 0 pairs bin 0 with itself
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             const float pm = 4.0f * (pk::re(sq) + pk::im(sq));
             p2 = (tid == 0) ? pm : p2;
         }
-        pk::c64 m = pk::mul(pk::make(sqrt_mufu(p1), sqrt_mufu(p2)), pk::make(p.coef_half, p.coef_half));
+        pk::c64 m = pk::mul(pk::make(fast::sqrt_approx(p1), fast::sqrt_approx(p2)), pk::make(p.coef_half, p.coef_half));
         if(XF && p.slope != nullptr)
             m = pk::mul(m, pk::make(__ldg(p.slope + k1), __ldg(p.slope + ((j == 0) ? k2_first : k2_base - j * TN))));
         pk::split(m, m1, m2);
@@ -506,7 +507,21 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
             return outv;
         };
         const bool all_proc = proc[0] && (CC == 1 || proc[1]);
-        if(!last_silent && all_proc)
+        if(R == 1 && CC == 1 && !XF && !last_silent && all_proc)
+        {
+            // hot path of the one-CTA-per-stream, one-channel kernel: dB of a bin pair with one packed multiply
+            float omax = -INFINITY;
+#pragma unroll
+            for(int j = 0; j < NST / 2; ++j)
+            {
+                float d1, d2;
+                pk::split(fast::dbfs2(st[0][2 * j], st[0][2 * j + 1], p.db_min), d1, d2);
+                emit(0, bin_of(2 * j), d1, omax);
+                emit(0, bin_of(2 * j + 1), d2, omax);
+            }
+            outs0 = !(omax > p.floor_m10);
+        }
+        else if(!last_silent && all_proc)
         {
             // hot path: every channel processed this tick — straight-line code
             for(int d = 0; d < dch; ++d)
@@ -644,13 +659,21 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                 proc[c] = do_proc;
                 const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);
                 const pk::c64 *twp = reinterpret_cast<const pk::c64 *>(p.tw_post) + tid;
-#pragma unroll
-                for(int j = 0; j < HP; ++j)
+                if(do_proc) // block-uniform: a channel that is not processed keeps its state and needs no split pass
                 {
-                    float m1, m2;
-                    split_pair(X, twp, j, m1, m2);
-                    ema(m1, st[c][2 * j], do_proc);
-                    ema(m2, st[c][2 * j + 1], do_proc);
+#pragma unroll
+                    for(int j = 0; j < HP; ++j)
+                    {
+                        float m1, m2;
+                        split_pair(X, twp, j, m1, m2);
+                        // EMA of the pair, two roundings per bin as the generic reference (src/source_generic.cpp:130), packed
+                        pk::c64 old = pk::make(st[c][2 * j], st[c][2 * j + 1]);
+                        pk::c64 m = pk::make(m1, m2);
+                        if(XF && p.fast_peaks)
+                            old = pk::make(fmaxf(m1, st[c][2 * j]), fmaxf(m2, st[c][2 * j + 1]));
+                        m = pk::add(pk::mul(pk::make(ema_g, ema_g), old), pk::mul(pk::make(ema_g2, ema_g2), m));
+                        pk::split(m, st[c][2 * j], st[c][2 * j + 1]);
+                    }
                 }
             }
             do_outputs(t, 0, proc);
@@ -743,9 +766,12 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                 {
                     const bool do_proc = gate_channel(c, ((nzb >> c) & 1u) != 0, skip_all, proc, silent_channels);
                     proc[c] = do_proc;
+                    if(do_proc) // cluster-uniform: an unprocessed channel keeps its state
+                    {
 #pragma unroll
-                    for(int i = 0; i < NST; ++i)
-                        ema(inbox[(f * CC + c) * SLICE + tid + i * TN], st[c][i], do_proc);
+                        for(int i = 0; i < NST; ++i)
+                            ema(inbox[(f * CC + c) * SLICE + tid + i * TN], st[c][i]);
+                    }
                 }
                 do_outputs(t, f, proc);
             }
