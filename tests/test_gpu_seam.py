@@ -43,7 +43,9 @@ def test_wavsource_cuda_matches_wavsource_generic_tick_for_tick(settings, channe
     assert a["frames"] == b["frames"] == T
     assert np.array_equal(a["silent"], b["silent"])
     rep = parity_report(b["db"], a["db"], db_min=gen.db_min)
-    assert rep["ok"] and rep["normwise"] < 1e-6, rep
+    # two independent fp32 FFTs (FFTW's codelets vs the CUDA passes), each ~4e-7 from a double-precision DFT
+    # (tests/test_gpu_scale.py::test_fp64_arbiter_*): up to 1.3e-6 from each other over 40 ticks
+    assert rep["ok"] and rep["normwise"] < 2e-6, rep
 
 
 def test_wavsource_cuda_volume_normalisation_live_rms_and_hide_show():

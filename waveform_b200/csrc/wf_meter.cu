@@ -39,6 +39,8 @@ struct MParams {
     const float *hist;   // [streams][cc][W] time-ordered ring contents before this call
     float *hist_next;    // same layout, after this call
     float *partial;      // [streams][pc][nblk]
+    const float *part_in; // one-pass path: the W/hop block partials of the ring as the previous call left them, or null (reduce the ring)
+    float *part_out;      // one-pass path: this call's last W/hop block partials [streams][pc][W/hop]
     float *raw;          // [streams][ticks][pc]
     float *buf;          // [streams][2] m_meter_buf
     unsigned char *flags;// [streams] m_last_silent
@@ -308,9 +310,17 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const bool two = (MODE == WF_METER_INPUT_RMS) && cc > 1;
     const int q4 = hop >> 2;
+    // history blocks whose partials the previous call left behind (same hop): no need to read the ring again, unless the block
+    // stays in the window beyond this call (T < W/hop) and therefore has to be copied into the next ring
+    const bool have_part = p.part_in != nullptr;
+    if(have_part)
+        for(int i = threadIdx.x; i < pc * nb; i += blockDim.x)
+            part[(i / nb) * NB + (i % nb)] = p.part_in[(size_t)s * pc * nb + i];
     for(int w = warp; w < pc * NB; w += nwarps)
     {
         const int c = w / NB, b = w - c * NB;
+        if(have_part && b < nb && b < T)
+            continue;
         const Row r0 = row_of(p, s, c);
         const Row r1 = two ? row_of(p, s, 1) : r0;
         const float4 *src0 = reinterpret_cast<const float4 *>((b < nb) ? r0.hist + (size_t)b * hop : r0.pcm + (size_t)(b - nb) * hop);
@@ -354,10 +364,12 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
             }
         }
         acc = warp_combine<MODE>(acc);
-        if(lane == 0)
+        if(lane == 0 && !(have_part && b < nb))
             part[c * NB + b] = acc;
     }
     __syncthreads();
+    for(int i = threadIdx.x; i < pc * nb; i += blockDim.x) // the ring's partials for the next call
+        p.part_out[(size_t)s * pc * nb + i] = part[(i / nb) * NB + T + (i % nb)];
     // window of tick t = blocks [t+1, t+1+nb)
     for(int idx = threadIdx.x; idx < T * pc; idx += blockDim.x)
     {
@@ -453,6 +465,10 @@ struct wf_meter {
     int64_t launches = 0;
     float *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
+    // one-pass path: block partials of the ring, double-buffered like the ring; valid for `part_hop` (0 = not valid: reduce the ring)
+    float *d_part[2] = {nullptr, nullptr};
+    size_t part_cap = 0;
+    int part_hop = 0, part_cur = 0;
     bool use_fused = true; // WF_METER_FUSED=0: always the three-kernel path (A/B tests)
     float *d_buf = nullptr;
     unsigned char *d_flags = nullptr;
@@ -634,7 +650,7 @@ void wf_meter_destroy(wf_meter *m)
         cudaSetDevice(m->device);
         cudaStreamSynchronize(m->stream);
     }
-    void *ptrs[] = {m->d_hist[0], m->d_hist[1], m->d_buf, m->d_flags, m->d_partial, m->d_raw,
+    void *ptrs[] = {m->d_part[0], m->d_part[1], m->d_hist[0], m->d_hist[1], m->d_buf, m->d_flags, m->d_partial, m->d_raw,
                     m->s_pcm, m->s_db, m->s_lin, m->s_silent};
     for(void *q : ptrs)
         if(q)
@@ -772,6 +788,26 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     {
         p.bl = b->hop;
         p.nblk = (int)(W / b->hop + T);
+        // partial state: [max_streams][pc][W/hop] x 2; usable when the previous call was a one-pass call with this hop that
+        // covered every stream (a reset or a general-path call invalidates it: the ring is then reduced again)
+        const size_t nbk = (size_t)(W / b->hop), need = (size_t)m->cfg.max_streams * pc * nbk;
+        if(need > m->part_cap)
+        {
+            for(auto &q : m->d_part)
+            {
+                if(q)
+                    cudaFree(q);
+                q = nullptr;
+                WFM_CUDA(m, cudaMalloc((void **)&q, need * sizeof(float)));
+            }
+            m->part_cap = need;
+            m->part_hop = 0;
+        }
+        const bool whole = (b->first_stream == 0) && (b->n_streams == m->cfg.max_streams);
+        p.part_in = (m->part_hop == b->hop && whole) ? m->d_part[m->part_cur] : nullptr;
+        p.part_out = m->d_part[m->part_cur ^ 1] + slot * pc * nbk;
+        m->part_cur ^= 1;
+        m->part_hop = whole ? b->hop : 0;
         auto launch = [&](auto kernel) -> cudaError_t {
             if(fused_smem > 48 * 1024)
             {
@@ -792,6 +828,7 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
     }
     else
     {
+    m->part_hop = 0; // the general path does not maintain the block partials
     const int g1 = grid_for((long long)S * pc * nchunk, kWarps, m->sm_count), g2 = grid_for((long long)S * T * pc, kWarps, m->sm_count);
     switch(m->cfg.mode)
     {
@@ -858,6 +895,7 @@ int wf_meter_reset(wf_meter *m, int32_t first, int32_t count)
     if(count == 0)
         return WF_OK;
     WFM_CUDA(m, cudaSetDevice(m->device));
+    m->part_hop = 0; // the ring of some streams is zeroed: their block partials are reduced from it again on the next call
     meter_reset_kernel<<<std::min(count, m->sm_count * 4), 256, 0, m->stream>>>(m->d_hist[m->cur], m->d_buf, m->d_flags, first,
                                                                              count, m->cfg.capture_channels, m->W);
     WFM_CUDA(m, cudaGetLastError());

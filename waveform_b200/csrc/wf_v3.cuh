@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
         float oldval = state;
         if(XF && p.fast_peaks)
             oldval = fmaxf(mag, oldval);
-        state = __fadd_rn(__fmul_rn(ema_g, oldval), __fmul_rn(ema_g2, mag));
+        state = __fmaf_rn(ema_g, oldval, __fmul_rn(ema_g2, mag)); // one fused rounding, see the R == 1 flow
     };
     // split pass of pair j of my tick -> (|X[k1]|, |X[k2]|), normalised, slope applied (src/source_generic.cpp:110-122)
     auto split_pair = [&](const pk::c64 *X, const pk::c64 *twp, int j, float &m1, float &m2) {
@@ -666,12 +666,15 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
                     {
                         float m1, m2;
                         split_pair(X, twp, j, m1, m2);
-                        // EMA of the pair, two roundings per bin as the generic reference (src/source_generic.cpp:130), packed
+                        // EMA of the pair, packed: g*old + (g2*mag) with ONE fused rounding on the first product, as
+                        // wf_fast2048.cuh and the reference's AVX2 path (src/source_avx2.cpp:154); the cluster flow's scalar
+                        // ema() below uses the same form, so R = 1 and R > 1 stay bit-identical.  (ptxas contracts a packed
+                        // mul.rn + add.rn pair into FFMA2 anyway: the two-rounding form cannot be expressed in f32x2.)
                         pk::c64 old = pk::make(st[c][2 * j], st[c][2 * j + 1]);
                         pk::c64 m = pk::make(m1, m2);
                         if(XF && p.fast_peaks)
                             old = pk::make(fmaxf(m1, st[c][2 * j]), fmaxf(m2, st[c][2 * j + 1]));
-                        m = pk::add(pk::mul(pk::make(ema_g, ema_g), old), pk::mul(pk::make(ema_g2, ema_g2), m));
+                        m = pk::fma(pk::make(ema_g, ema_g), old, pk::mul(pk::make(ema_g2, ema_g2), m));
                         pk::split(m, st[c][2 * j], st[c][2 * j + 1]);
                     }
                 }
