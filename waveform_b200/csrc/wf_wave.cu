@@ -57,67 +57,19 @@ __global__ void __launch_bounds__(256) wave_kernel(const WParams p)
         const float *pcm0 = p.pcm + (size_t)s * p.stream_stride;
         const float *pcm1 = pcm0 + p.channel_stride;
         __syncthreads();
-        // The new points of tick t+1 (index table + gathered samples: two dependent global loads) are fetched into registers
-        // while tick t is processed: the per-tick critical path was those two latencies with ~cnt of 256 threads active.
-        constexpr int kPre = 4; // points per thread held ahead (cnt <= 4 * 256; larger ticks load in place)
-        float pre0[kPre], pre1[kPre];
-        auto prefetch = [&](int t) {
-            if(t >= p.n_ticks)
-                return;
-            const int o0 = p.off[t], cnt = p.off[t + 1] - o0;
-            if(cnt > kPre * nt)
-                return;
-#pragma unroll
-            for(int u = 0; u < kPre; ++u)
-            {
-                const int i = tid + u * nt;
-                pre0[u] = pre1[u] = 0.0f;
-                if(i < cnt)
-                {
-                    const int q = __ldg(p.src + o0 + i);
-                    if(q >= 0)
-                    {
-                        pre0[u] = __ldg(pcm0 + q);
-                        if(p.cc > 1)
-                            pre1[u] = __ldg(pcm1 + q);
-                    }
-                }
-            }
-        };
-        prefetch(0);
         for(int t = 0; t < p.n_ticks; ++t)
         {
             const int o0 = p.off[t], cnt = p.off[t + 1] - o0;
             // the cnt oldest points are replaced by the new raw samples, then the ring rotates (src/source_generic.cpp:333-339)
-            if(cnt <= kPre * nt)
+            for(int i = tid; i < cnt; i += nt)
             {
-#pragma unroll
-                for(int u = 0; u < kPre; ++u)
-                {
-                    const int i = tid + u * nt;
-                    if(i < cnt)
-                    {
-                        int pos = head + i;
-                        pos -= (pos >= W) ? W : 0;
-                        r0[pos] = pre0[u];
-                        if(p.cc > 1)
-                            r1[pos] = pre1[u];
-                    }
-                }
+                const int q = __ldg(p.src + o0 + i);
+                int pos = head + i;
+                pos -= (pos >= W) ? W : 0;
+                r0[pos] = (q >= 0) ? __ldg(pcm0 + q) : 0.0f;
+                if(p.cc > 1)
+                    r1[pos] = (q >= 0) ? __ldg(pcm1 + q) : 0.0f;
             }
-            else
-            {
-                for(int i = tid; i < cnt; i += nt)
-                {
-                    const int q = __ldg(p.src + o0 + i);
-                    int pos = head + i;
-                    pos -= (pos >= W) ? W : 0;
-                    r0[pos] = (q >= 0) ? __ldg(pcm0 + q) : 0.0f;
-                    if(p.cc > 1)
-                        r1[pos] = (q >= 0) ? __ldg(pcm1 + q) : 0.0f;
-                }
-            }
-            prefetch(t + 1);
             head += cnt;
             head -= (head >= W) ? W : 0;
             __syncthreads();
