@@ -14,10 +14,17 @@ CASES = [({"fft_size": 2048}, 1, 20, 3, 1, False),
          ({"fft_size": 800}, 1, 3, 3, 1, True),
          ({"fft_size": 256}, 1, 9, 3, 1, True),
          ({"fft_size": 128, "channel_mode": "stereo"}, 2, 17, 2, 1, True),
-         ({"fft_size": 16384}, 1, 2, 2, 2, False)]
+         ({"fft_size": 16384}, 1, 2, 2, 2, False),
+         # round 2: team kernel (few streams x many ticks, gate traffic), warp2 plans with radix 5 / 3 / 7 / 13 butterflies
+         ({"fft_size": 2048, "gravity": 0.3, "floor": -40}, 1, 3, 37, 1, False),
+         ({"fft_size": 800}, 1, 40, 5, 1, False),
+         ({"fft_size": 1920, "slope": 0.5, "fast_peaks": True}, 1, 9, 4, 2, False),
+         ({"fft_size": 1456}, 1, 5, 3, 1, False)]
 for s, ch, S, T, hopdiv, pts in CASES:
     e = Engine(s, channels=ch, max_streams=S); N = e.fft_size; hop = N // hopdiv
     x = synth_pcm(S, e.capture_channels, (T - 1) * hop + N); x[0, :, :] = 0
+    if T > 20:
+        x[1, :, 4 * hop:] = 0   # decay -> freeze: the team kernel's lazy team-wide gate reduction
     rms = np.full((S, T), 0.1, np.float32) if s.get("normalize_volume") else None
     o = e.process(torch.from_numpy(x).cuda(), T, hop, want_points=pts, want_peak=True,
                   input_rms=None if rms is None else torch.from_numpy(rms))
@@ -30,11 +37,12 @@ for s, ch, S, T, hopdiv, pts in CASES:
 from waveform_b200 import MeterEngine, WaveEngine
 from waveform_b200.engine import METER_INPUT_RMS
 for mode, st in ((None, {"meter_buf": 20, "rms_mode": True}), (None, {"meter_buf": 50, "rms_mode": False}), (METER_INPUT_RMS, {})):
-    m = MeterEngine(st, channels=2, max_streams=3, mode=mode)
-    x = synth_pcm(3, 2, 9 * 441)
-    a = m.process(x[:, :, : 4 * 441], 4, 441); b = m.process(torch.from_numpy(x[:, :, 4 * 441:]).cuda(), 5, 441)
-    torch.cuda.synchronize()
-    print("meter", mode, "ok", flush=True)
+    for hop in (441, 480):   # 441: three-kernel path; 480 divides the windows (960 / 2400 / 48000): one-pass path, partials carried
+        m = MeterEngine(st, channels=2, max_streams=3, mode=mode)
+        x = synth_pcm(3, 2, 9 * hop)
+        a = m.process(x[:, :, : 4 * hop], 4, hop); b = m.process(torch.from_numpy(x[:, :, 4 * hop:]).cuda(), 5, hop)
+        torch.cuda.synchronize()
+        print("meter", mode, hop, "ok", flush=True)
 for st, ch in (({"width": 300, "meter_buf": 50, "channel_mode": "stereo"}, 2), ({"width": 200, "meter_buf": 10}, 1)):
     w = WaveEngine(st, channels=ch, max_streams=3)
     x = synth_pcm(3, ch, 9 * 800)
