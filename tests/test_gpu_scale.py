@@ -375,3 +375,57 @@ def test_per_tick_seconds_tv_exponential(N, S, team_w, monkeypatch):
             o.tick([pcm[s, 0, t * N:(t + 1) * N]], float(secs[t]))
             rep = parity_report(out["db"][s, t], np.stack([o.decibels(0)]), db_min=eng.db_min)
             assert rep["ok"] and rep["normwise"] < 1e-6, (eng.last_kernel_name(), s, t, rep)
+
+
+@pytest.mark.parametrize("variant", ["plain", "options", "odd_hop"])
+def test_par16384_bin_parity_cluster(variant, monkeypatch):
+    """wf_par16384.cuh (N = 16384: a cluster of two CTAs per stream, even / odd bins, each on the N=8192 plan): parity against
+    the oracle incl. the gate's freeze / wake-up across a call boundary (cluster-wide flag reduction), skip mask, per-tick
+    gravity, the option set and the peak output; agreement with the CTA-per-tick kernel it replaces."""
+    import torch
+    from waveform_b200 import Engine
+
+    N = 16384
+    if variant == "options":
+        settings = {"fft_size": N, "window": "blackman_harris", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0, "fast_peaks": True,
+                    "temporal_smoothing": "tv_exp_moving_avg", "gravity": 0.5, "normalize_volume": True}
+    else:
+        settings = {"fft_size": N, "window": "hann", "gravity": 0.3, "floor": -40}
+    hop = N if variant != "odd_hop" else 4097   # an odd hop: scalar loads instead of 64-bit ones
+    S, T = 7, 24
+    pcm = synth_pcm(S, 1, (T - 1) * hop + N, zero_frames=[(1, 3, 7), (2, 0, 24), (5, 4, 24)], frame_len=N, hop=hop)
+    if variant != "odd_hop":
+        pcm[5, :, 18 * N: 19 * N] = 0.1
+    rng = np.random.default_rng(4)
+    rms = (0.02 + 0.3 * rng.uniform(size=(S, T))).astype(np.float32) if variant == "options" else None
+    secs = (1.0 / 60.0 * (0.5 + rng.uniform(size=T))).astype(np.float32) if variant == "options" else None
+    skip = (rng.uniform(size=(S, T)) < 0.08).astype(np.uint8) if variant == "options" else None
+    x = torch.from_numpy(pcm).cuda()
+    outs = {}
+    for name, flag in (("par", "1"), ("v3", "0")):
+        monkeypatch.setenv("WF_PAR16384", flag)
+        eng = Engine(settings, channels=1, max_streams=S)
+
+        def kw(a, b):
+            return dict(input_rms=None if rms is None else torch.from_numpy(rms[:, a:b].copy()).cuda(),
+                        skip_mask=None if skip is None else torch.from_numpy(skip[:, a:b].copy()).cuda(),
+                        frame_seconds=None if secs is None else secs[a:b], want_peak=True)
+        a = eng.process(x[:, :, : 8 * hop + N].contiguous(), 9, hop, **kw(0, 9))
+        b = eng.process(x[:, :, 9 * hop:].contiguous(), T - 9, hop, **kw(9, T))
+        torch.cuda.synchronize()
+        want = "stft16384_parity_kernel" if name == "par" else "stft_v3_kernel<16384"
+        assert eng.last_kernel_name().startswith(want), eng.last_kernel_name()
+        outs[name] = ({k: torch.cat([a[k], b[k]], dim=1 if k != "peak" else 0).cpu().numpy() for k in ("db", "silent", "peak")},
+                      eng.get_state())
+    got, st = outs["par"]
+    assert np.array_equal(got["silent"], outs["v3"][0]["silent"])
+    rep = parity_report(got["db"], outs["v3"][0]["db"], db_min=-758.0)
+    assert rep["ok"], rep
+    assert np.allclose(got["peak"], outs["v3"][0]["peak"], atol=2e-3)
+    assert np.array_equal(st["flags"], outs["v3"][1]["flags"])
+    if variant != "options":
+        ref_db, _, ref_sil = _oracle_rows(settings, 1, pcm, T, hop)
+        assert np.array_equal(got["silent"], ref_sil) and ref_sil.sum() > 10
+        rep = parity_report(got["db"], ref_db, db_min=-758.0)
+        assert rep["ok"] and rep["normwise"] < 2e-6, rep
+        assert parity_report(st["hold_db"][:, 0], ref_db[:, -1, 0], db_min=-758.0)["ok"]   # m_decibels mirror after the call

@@ -24,6 +24,7 @@
 #include "wf_v3.hpp"
 #include "wf_team2048.hpp"
 #include "wf_warp2.hpp"
+#include "wf_par16384.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -40,6 +41,7 @@ struct wf_engine {
     int64_t launches = 0;
     std::string last_kernel;    // name of the spectrum kernel the most recent launch_range dispatched to (wf_last_kernel_name)
     bool hold_implicit = false; // some stream may carry flags bit 3 (m_decibels mirror left implicit by the N=2048 kernel)
+    bool use_par16384 = true;   // WF_PAR16384=0: N=16384 stays on the CTA-per-tick kernel (A/B tests)
     bool use_warp2 = true;      // WF_WARP2=0: non-power-of-two sizes stay on the first-generation any-N kernel (A/B tests)
     bool lazy_hold = true;      // WF_LAZY_HOLD=0: always write the mirror (A/B tests)
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
@@ -580,6 +582,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
             e->team_w = atoi(tw);
         const char *zc = getenv("WF_ZERO_COPY");
         e->zero_copy = !(zc && zc[0] == '0');
+        const char *p16 = getenv("WF_PAR16384");
+        e->use_par16384 = !(p16 && p16[0] == '0');
         const char *w2 = getenv("WF_WARP2");
         e->use_warp2 = !(w2 && w2[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
@@ -898,6 +902,17 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         const int rc = materialize_hold(e, st); // the other kernels read hold_db as it is
         if(rc)
             return rc;
+    }
+    // N = 16384 (config 5): a cluster of two CTAs per stream splits the bins by parity, each on the spill-free N=8192 plan
+    const bool par_ok = (N == 16384) && e->use_par16384 && e->use_v3 && e->d_tw0 && (cc == 1) && !t.cfg.stereo && kp.out_db &&
+                        !kp.out_points && !kp.out_pixels && !kp.out_min && !e->force_generic;
+    if(par_ok)
+    {
+        const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
+        WF_CUDA(e, par16384_launch(x, kp, e->d_tw1, e->d_tw2, e->d_tw0, st, e->device));
+        e->launches++;
+        e->last_kernel = "stft16384_parity_kernel<" + std::to_string((int)x) + "> " + std::to_string(kp.n_streams) + " clusters of 2";
+        return WF_OK;
     }
     // Non-power-of-two sizes with a compiled two-pass plan (wf_warp2.cuh): same launch shape as the N=2048 kernel.
     const bool warp2_ok = e->use_warp2 && warp2_supported(N) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points &&

@@ -284,21 +284,21 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
                             d2 = fmaxf(d2 - __ldg(p.rolloff + k2c), p.db_min);
                         }
                     }
+                    // idle lanes (lane >= P) run the same arithmetic on don't-care values; only the stores are predicated and
+                    // the lane's flags are discarded after the loop (no branches inside the unrolled epilogue)
                     const bool st2 = act_b && (k2 >= 0);
+                    if(k1 >= 1)
+                        peak = fmaxf(peak, d1);
+                    outs &= !(d1 > p.floor_m10);
                     if(act_b)
-                    {
-                        if(k1 >= 1)
-                            peak = fmaxf(peak, d1);
-                        outs &= !(d1 > p.floor_m10);
                         stg_stream(odb + k1, d1);
-                    }
+                    peak = (k2 >= 0) ? fmaxf(peak, d2) : peak;
+                    outs &= (k2 < 0) | !(d2 > p.floor_m10);
                     if(st2)
-                    {
-                        peak = fmaxf(peak, d2);
-                        outs &= !(d2 > p.floor_m10);
-                        stg_stream(odb + k2, d2);
-                    }
+                        stg_stream(odb + k2c, d2);
                 });
+                outs |= !act_b;
+                peak = act_b ? peak : -INFINITY;
             }
             else
             {
