@@ -25,6 +25,7 @@
 #include "wf_team2048.hpp"
 #include "wf_warp2.hpp"
 #include "wf_par16384.hpp"
+#include "wf_nvtx.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -935,6 +936,7 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
 {
     if(!e || !b)
         return WF_ERR_INVALID_ARG;
+    NvtxRange nvtx("wf_process");
     if(b->struct_size != sizeof(wf_batch))
         return set_err(e, WF_ERR_ABI, "wf_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_batch));
     const Tables &t = e->tab;
@@ -1279,6 +1281,7 @@ int wf_peak_normalize(wf_engine *e, float *data, int32_t n_streams, int32_t n_fr
 {
     if(!e || !data || !peak || n_streams < 0 || n_frames < 0 || row_len < 1)
         return e ? set_err(e, WF_ERR_INVALID_ARG, "bad peak_normalize arguments") : WF_ERR_INVALID_ARG;
+    NvtxRange nvtx("wf_peak_normalize");
     if(n_streams == 0 || n_frames == 0)
         return WF_OK;
     WF_CUDA(e, cudaSetDevice(e->device));

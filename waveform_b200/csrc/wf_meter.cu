@@ -26,6 +26,7 @@
 #include <new>
 #include <string>
 
+#include "wf_nvtx.hpp"
 #include "wf_tables.hpp"
 #include "wfstft.h"
 
@@ -670,6 +671,7 @@ int wf_meter_process_async(wf_meter *m, const wf_meter_batch *b, void *cuda_stre
 {
     if(!m || !b)
         return WF_ERR_INVALID_ARG;
+    wf::NvtxRange nvtx("wf_meter_process");
     if(b->struct_size != sizeof(wf_meter_batch))
         return merr(m, WF_ERR_ABI, "wf_meter_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_meter_batch));
     if(b->n_streams < 0 || b->n_ticks < 0 || b->hop < 1)

@@ -7,7 +7,16 @@ namespace wf {
 template<bool EXTRA>
 static cudaError_t launch(const KParams &kp, const v3::Tw3 &tw, cudaStream_t st, int device)
 {
-    (void)device; // 35 KB of dynamic shared memory: below the 48 KB default, no attribute needed
+    static thread_local bool configured[64] = {false};
+    const int dev = device & 63;
+    if(!configured[dev])
+    {
+        cudaError_t err = cudaFuncSetAttribute(stft16384_parity_kernel<EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)par16384::smem_bytes());
+        if(err != cudaSuccess)
+            return err;
+        configured[dev] = true;
+    }
     stft16384_parity_kernel<EXTRA><<<dim3((unsigned)(2 * kp.n_streams)), par16384::kTN, par16384::smem_bytes(), st>>>(kp, tw);
     return cudaGetLastError();
 }

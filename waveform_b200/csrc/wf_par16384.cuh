@@ -14,6 +14,8 @@
 // thread, 256 threads, three register passes, every shared-memory access base + immediate (wf_v3.cuh).
 // Semantics: src/source_generic.cpp:26-180 as restated in wf_fast2048.cuh / wf_v3.cuh.
 #pragma once
+#include <cstdint>
+
 #include "wf_v3.cuh"
 
 namespace wf {
@@ -25,7 +27,9 @@ using G = v3::Geo3<8192>;
 constexpr int kTN = G::TN;       // 256 threads
 constexpr int kP = G::P;         // 16 points (= bins) per thread
 constexpr int kHP = kP / 2;      // bin pairs per thread
-constexpr size_t smem_bytes() { return (size_t)G::BUF * sizeof(float2); }
+constexpr size_t kBufBytes = (((size_t)G::BUF * sizeof(float2)) + 127) / 128 * 128;
+constexpr size_t kStageBytes = (size_t)kN * sizeof(float); // the whole frame, TMA-staged one tick ahead
+constexpr size_t smem_bytes() { return kBufBytes + kStageBytes + 16; }
 } // namespace par16384
 
 template<bool EXTRA>
@@ -37,6 +41,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
     constexpr int B = kBins, TN = kTN, P = kP, HP = kHP, MS = kSub;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
+    const pk::c64 *stage = reinterpret_cast<const pk::c64 *>(smem_raw + kBufBytes); // frame t: pairs z[n], n < 8192
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + kBufBytes + kStageBytes);
     __shared__ unsigned redf[2][2]; // [parity of the exchange][rank]: this rank's "all my outputs <= floor-10 dB"
     const int tid = threadIdx.x;
     const int r = (int)cluster_ctarank(); // 0: even bins, 1: odd bins
@@ -84,10 +90,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
         pos_valid = true;
     };
 
+    // TMA staging (cp.async.bulk + mbarrier) needs 16-byte aligned frames; otherwise the frame is loaded straight from global
+    const bool use_tma = (((uintptr_t)pcm_s & 15u) == 0) && ((p.hop & 3) == 0);
+    uint32_t phase = 0;
+    if(tid == 0)
+    {
+        fast::mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if(use_tma && T > 0 && tid == 0)
+    {
+        fast::mbar_expect_tx(mbar, (uint32_t)kStageBytes);
+        fast::tma_load_1d(const_cast<pk::c64 *>(stage), pcm_s, (uint32_t)kStageBytes, mbar);
+    }
     const pk::c64 *win = reinterpret_cast<const pk::c64 *>(p.window2) + tid; // pairs (w[2n], w[2n+1]), n = a*TN + tid
     const pk::c64 *tw0 = reinterpret_cast<const pk::c64 *>(tw.tw0) + tid;    // W_8192^(a*TN + tid)
     const pk::c64 *twp = reinterpret_cast<const pk::c64 *>(p.tw_post);       // W_16384^k, k < 8192
-    if(T > 0)
+    if(!use_tma && T > 0)
         F::prefetch_l2(pcm_s, tid), F::prefetch_l2(pcm_s + kN / 2, tid);
 
 #pragma unroll 1
@@ -97,6 +117,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
         // ---- both halves of the frame, window, radix-2 first stage for MY parity ----
         pk::c64 x[P];
         unsigned long long nzbits = 0;
+        if(use_tma)
+        {
+            fast::mbar_wait(mbar, phase);
+            phase ^= 1u;
+            // (the rank test sits outside the unrolled loops: inside, ptxas if-converts both variants into predicated code)
+            if(r == 0)
+            {
+#pragma unroll
+                for(int a = 0; a < P; ++a)
+                {
+                    pk::c64 za = stage[a * TN + tid], zb = stage[MS + a * TN + tid];
+                    nzbits |= za | zb;
+                    if(p.window2 != nullptr)
+                    {
+                        za = pk::mul(za, __ldg(win + a * TN));
+                        zb = pk::mul(zb, __ldg(win + MS + a * TN));
+                    }
+                    x[a] = pk::add(za, zb);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for(int a = 0; a < P; ++a)
+                {
+                    pk::c64 za = stage[a * TN + tid], zb = stage[MS + a * TN + tid];
+                    nzbits |= za | zb;
+                    if(p.window2 != nullptr)
+                    {
+                        za = pk::mul(za, __ldg(win + a * TN));
+                        zb = pk::mul(zb, __ldg(win + MS + a * TN));
+                    }
+                    x[a] = pk::cmul(pk::sub(za, zb), __ldg(tw0 + a * TN));
+                }
+            }
+            __syncthreads(); // every thread has taken its samples: the staging area can receive the next frame
+            if(tid == 0 && t + 1 < T)
+            {
+                fast::fence_proxy_async();
+                fast::mbar_expect_tx(mbar, (uint32_t)kStageBytes);
+                fast::tma_load_1d(const_cast<pk::c64 *>(stage), frame + p.hop, (uint32_t)kStageBytes, mbar);
+            }
+        }
+        else
         {
             const float2 *lo = reinterpret_cast<const float2 *>(frame) + tid;
             const float2 *hi = lo + MS;
@@ -123,9 +187,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
                 }
                 x[a] = (r == 0) ? pk::add(za, zb) : pk::cmul(pk::sub(za, zb), __ldg(tw0 + a * TN));
             }
+            if(t + 1 < T) // next frame -> L2 while this one is transformed
+                F::prefetch_l2(frame + p.hop, tid), F::prefetch_l2(frame + p.hop + kN / 2, tid);
         }
-        if(t + 1 < T) // next frame -> L2 while this one is transformed (no register room for a register prefetch)
-            F::prefetch_l2(frame + p.hop, tid), F::prefetch_l2(frame + p.hop + kN / 2, tid);
         const bool nz = F::template run_core<1, true>(x, buf, tw, tid, (nzbits & 0x7fffffff7fffffffull) != 0ull,
                                                        reinterpret_cast<pk::c64 *>(buf));
         const pk::c64 *X = reinterpret_cast<const pk::c64 *>(buf);

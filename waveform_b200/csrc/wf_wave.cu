@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "wf_nvtx.hpp"
 #include "wfstft.h"
 
 namespace {
@@ -435,6 +436,7 @@ int wf_wave_process_async(wf_wave *w, const wf_wave_batch *b, void *cuda_stream)
 {
     if(!w || !b)
         return WF_ERR_INVALID_ARG;
+    wf::NvtxRange nvtx("wf_wave_process");
     if(b->struct_size != sizeof(wf_wave_batch))
         return werr(w, WF_ERR_ABI, "wf_wave_batch.struct_size %u != %zu", b->struct_size, sizeof(wf_wave_batch));
     if(b->n_ticks < 0 || b->hop < 1)
