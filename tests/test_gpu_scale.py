@@ -429,3 +429,39 @@ def test_par16384_bin_parity_cluster(variant, monkeypatch):
         rep = parity_report(got["db"], ref_db, db_min=-758.0)
         assert rep["ok"] and rep["normwise"] < 2e-6, rep
         assert parity_report(st["hold_db"][:, 0], ref_db[:, -1, 0], db_min=-758.0)["ok"]   # m_decibels mirror after the call
+
+
+def test_zero_copy_live_path_equals_staged_path(monkeypatch):
+    """wf_host_alloc: a small batch whose buffers all live in page-locked, device-mapped host memory is processed in place
+    (one launch, no staging copies — the live tick of host/source_cuda.hpp); the same call with WF_ZERO_COPY=0, and with
+    pageable numpy buffers, must give identical bits.  A batch above 1 MiB of PCM in the same kind of memory is staged."""
+    import ctypes as C
+    from waveform_b200 import Engine
+
+    N, cc = 4096, 2
+    settings = {"fft_size": N, "channel_mode": "stereo", "window": "blackman_harris"}
+    pcm = synth_pcm(1, cc, 6 * N, seed=2)[0]
+    outs = {}
+    for name, zc in (("zero_copy", "1"), ("staged", "0")):
+        monkeypatch.setenv("WF_ZERO_COPY", zc)
+        eng = Engine(settings, channels=cc, max_streams=1)
+        L, B, dch = eng.L, eng.bins, eng.display_channels
+        pin = L.wf_host_alloc(cc * N * 4)
+        pout = L.wf_host_alloc(dch * B * 4)
+        pfl = L.wf_host_alloc(16)
+        assert pin and pout and pfl
+        rows = []
+        launches0 = eng.launch_count
+        for t in range(6):
+            frame = np.ascontiguousarray(pcm[:, t * N:(t + 1) * N])
+            C.memmove(pin, frame.ctypes.data, frame.nbytes)
+            C.memset(pfl, 0, 16)
+            eng.process_raw(pin, 1, 1, N, cc * N, N, out_db=pout, out_silent=pfl + 1, skip_mask=pfl)
+            rows.append(np.ctypeslib.as_array(C.cast(pout, C.POINTER(C.c_float)), shape=(dch, B)).copy())
+        outs[name] = np.stack(rows)
+        assert eng.launch_count - launches0 == 6
+        for q in (pin, pout, pfl):
+            L.wf_host_free(q)
+    assert np.array_equal(outs["zero_copy"], outs["staged"])
+    ref = Engine(settings, channels=cc, max_streams=1).process(pcm[None], 6, N)["db"][0]
+    assert np.array_equal(outs["zero_copy"], ref)

@@ -80,7 +80,7 @@ struct wf_engine {
            s_silent_cap = 0;
     // zero-copy verdict of the last host-pointer batch (live ticks reuse the same buffers every call)
     const void *zc_ptrs[9] = {};
-    bool zc_ok = false, zc_valid = false;
+    bool zc_ok = false, zc_dev = false, zc_valid = false;
     bool zero_copy = true; // WF_ZERO_COPY=0: always stage host buffers through device memory
     // copy/compute pipeline for host-pointer batches
     static constexpr int kMaxChunks = 16;
@@ -985,23 +985,20 @@ int wf_process_async(wf_engine *e, const wf_batch *b, void *cuda_stream)
         // launch + one synchronisation.  Every buffer of the batch must be device-addressable for that.
         const void *ptrs[9] = {b->pcm, b->input_rms, b->skip_mask, b->out_db, b->out_points, b->out_silent, b->out_peak, b->out_pixels,
                                b->out_min};
-        if(e->zc_valid && memcmp(ptrs, e->zc_ptrs, sizeof(ptrs)) == 0 && e->zc_ok)
-            dev_ptrs = true; // same buffers as the last call, already classified
+        const bool small = S * T * (size_t)cc * (size_t)N * sizeof(float) <= (1u << 20);
+        if(e->zc_valid && memcmp(ptrs, e->zc_ptrs, sizeof(ptrs)) == 0)
+            dev_ptrs = e->zc_dev || (e->zc_ok && small && e->zero_copy); // same buffers as the last call, already classified
         else
         {
             const int kpcm = ptr_kind(b->pcm);
-            dev_ptrs = (kpcm == 1);
-            bool zc = false;
-            if(kpcm == 2 && e->zero_copy && S * T * (size_t)cc * (size_t)N * sizeof(float) <= (1u << 20))
-            {
-                zc = true;
-                for(int i = 1; i < 9 && zc; ++i)
-                    zc = (ptrs[i] == nullptr) || (ptr_kind(ptrs[i]) != 0);
-            }
+            bool zc = (kpcm == 2); // every buffer device-addressable?
+            for(int i = 1; i < 9 && zc; ++i)
+                zc = (ptrs[i] == nullptr) || (ptr_kind(ptrs[i]) != 0);
             memcpy(e->zc_ptrs, ptrs, sizeof(ptrs));
+            e->zc_dev = (kpcm == 1);
             e->zc_ok = zc;
             e->zc_valid = true;
-            dev_ptrs = dev_ptrs || zc;
+            dev_ptrs = e->zc_dev || (zc && small && e->zero_copy);
         }
     }
 

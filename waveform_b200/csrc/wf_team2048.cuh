@@ -241,8 +241,122 @@ __global__ void __launch_bounds__(team::kWarps * 32, 1) stft2048_team_kernel(con
             team::bar_sync(bar_id, W * 32);
 
             // =================== phase 2: this warp's bin slice through the round's ticks, in order ===================
+            // Common case — a full round, every frame has signal, no skip mask: straight-line code for the W ticks (the
+            // loads of all ticks issue up front, only the EMA chain is serial), no per-tick gate logic.
+            bool round_done = false;
+            if(t0 + W <= T && !(EXTRA && p.skip_mask != nullptr))
+            {
+                bool all_nz = true;
+#pragma unroll
+                for(int i = 0; i < W; ++i)
+                    all_nz &= ctl_nz[i] != 0;
+                if(all_nz)
+                {
+                    last_silent = false;
+                    float *odb0 = p.out_db + ((size_t)s * T + t0) * B + b0;
+                    float dl[BPL]; // dB of the round's last tick (gate flags)
+#pragma unroll
+                    for(int i = 0; i < W; ++i)
+                    {
+                        const int tt = t0 + i;
+                        const float2 gt = (EXTRA && p.g_tab != nullptr) ? __ldg(p.g_tab + tt) : make_float2(p.g, p.g2);
+                        const float *mg = reinterpret_cast<const float *>(warps_base + (size_t)(tm * W + i) * kWarpBytes + kWarpBufBytes) + b0;
+                        float d[BPL];
+#pragma unroll
+                        for(int j = 0; j < BPL; j += VEC)
+                        {
+                            float m[4];
+                            if constexpr(VEC == 4)
+                            {
+                                const float4 x = *reinterpret_cast<const float4 *>(mg + j);
+                                m[0] = x.x, m[1] = x.y, m[2] = x.z, m[3] = x.w;
+                            }
+                            else
+                            {
+                                const float2 x = *reinterpret_cast<const float2 *>(mg + j);
+                                m[0] = x.x, m[1] = x.y;
+                            }
+#pragma unroll
+                            for(int u = 0; u < VEC; ++u)
+                            {
+                                float mm = m[u];
+                                if(tsm)
+                                {
+                                    float old = st[j + u];
+                                    if(EXTRA && p.fast_peaks)
+                                        old = fmaxf(mm, old);
+                                    mm = fmaf(gt.x, old, gt.y * mm);
+                                }
+                                st[j + u] = mm;
+                            }
+                        }
+#pragma unroll
+                        for(int j = 0; j < BPL; j += 2)
+                            pk::split(dbfs2(st[j], st[j + 1], p.db_min), d[j], d[j + 1]);
+                        if(EXTRA)
+                        {
+                            float vc = 0.0f;
+                            if(p.normalize)
+                            {
+                                const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * T + tt] : 0.0f;
+                                vc = fminf(p.vol_target - dbfs(rms, p.db_min), p.max_gain);
+                            }
+                            float peak = -INFINITY;
+#pragma unroll
+                            for(int j = 0; j < BPL; ++j)
+                            {
+                                const int k = b0 + j;
+                                if(k >= 1)
+                                {
+                                    if(p.normalize)
+                                        d[j] += vc;
+                                    if(p.rolloff != nullptr)
+                                        d[j] = fmaxf(d[j] - __ldg(p.rolloff + k), p.db_min);
+                                    peak = fmaxf(peak, d[j]);
+                                }
+                            }
+                            if(p.out_peak != nullptr)
+                            {
+                                const float gm = group_max<32>(peak, nullptr);
+                                if(lane == 0)
+                                    atomic_max_float(p.out_peak + tt, gm);
+                            }
+                        }
+                        float *odb = odb0 + (size_t)i * B;
+#pragma unroll
+                        for(int j = 0; j < BPL; j += VEC)
+                        {
+                            if constexpr(VEC == 4)
+                                asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(odb + j), "f"(d[j]), "f"(d[j + 1]),
+                                             "f"(d[j + 2]), "f"(d[j + 3])
+                                             : "memory");
+                            else
+                                asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(odb + j), "f"(d[j]), "f"(d[j + 1]) : "memory");
+                        }
+                        if(i == W - 1)
+                        {
+#pragma unroll
+                            for(int j = 0; j < BPL; ++j)
+                                dl[j] = d[j];
+                        }
+                    }
+                    if(gate)
+                    {
+                        bool outs = true;
+#pragma unroll
+                        for(int j = 0; j < BPL; ++j)
+                            outs &= !(dl[j] > p.floor_m10);
+                        outs_lane = outs;
+                        pos_valid = false;
+                    }
+                    if(p.out_silent != nullptr && wi == 0 && lane < W)
+                        p.out_silent[(size_t)s * T + t0 + lane] = 0;
+                    last_from_state = true;
+                    round_done = true;
+                }
+            }
 #pragma unroll 1
-            for(int i = 0; i < W; ++i)
+            for(int i = 0; i < W && !round_done; ++i)
             {
                 const int tt = t0 + i;
                 if(tt >= T)
