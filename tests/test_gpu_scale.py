@@ -465,3 +465,60 @@ def test_zero_copy_live_path_equals_staged_path(monkeypatch):
     assert np.array_equal(outs["zero_copy"], outs["staged"])
     ref = Engine(settings, channels=cc, max_streams=1).process(pcm[None], 6, N)["db"][0]
     assert np.array_equal(outs["zero_copy"], ref)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configs_against_oracle(seed):
+    """Differential fuzz over the whole dispatch table: random size (powers of two, mixed-radix plans, sizes without a plan),
+    window, channel mode, smoothing, options, hop, stream / tick counts (which select warp / team / cluster kernels), silent
+    stretches, skip masks, per-tick frame times and call boundaries — every draw must match the oracle tick for tick."""
+    from oracle.oraclebind import OracleSource
+    from waveform_b200 import Engine
+
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.choice([128, 512, 1024, 2048, 2048, 4096, 8192, 16384, 800, 720, 1600, 1920, 1456, 352, 2000, 4160, 1088]))
+    mode = str(rng.choice(["mono", "mono", "stereo"]))
+    channels = 2 if mode == "stereo" or rng.uniform() < 0.25 else 1
+    settings = {"fft_size": N, "channel_mode": mode,
+                "window": str(rng.choice(["none", "hann", "hamming", "blackman", "blackman_harris", "power_of_sine"])),
+                "temporal_smoothing": str(rng.choice(["none", "exp_moving_avg", "exp_moving_avg", "tv_exp_moving_avg"])),
+                "gravity": float(rng.choice([0.2, 0.5, 0.65, 0.9])), "floor": int(rng.choice([-30, -45, -65]))}
+    if rng.uniform() < 0.3:
+        settings.update(slope=float(rng.choice([0.25, 1.0])), fast_peaks=bool(rng.uniform() < 0.5))
+    if rng.uniform() < 0.3:
+        settings.update(rolloff_q=1.0, rolloff_rate=float(rng.choice([3.0, 9.0])))
+    hop = int(N // int(rng.choice([1, 1, 2, 4]))) if rng.uniform() < 0.8 else int(rng.integers(N // 4, N)) // 2 * 2 + 1  # odd hop sometimes
+    S = int(rng.choice([1, 3, 9, 40, 170]))
+    T = int(rng.choice([1, 5, 11, 23]))
+    eng = Engine(settings, channels=channels, max_streams=S)
+    cc = eng.capture_channels
+    ns = (T - 1) * hop + N
+    pcm = synth_pcm(min(S, 6), cc, ns, seed=seed)
+    for s in range(pcm.shape[0]):       # silent stretches: decay, freeze, wake-up
+        if rng.uniform() < 0.6:
+            a = int(rng.integers(0, ns // 2))
+            pcm[s, :, a: a + int(rng.integers(N, 4 * N + 1))] = 0.0
+    if S > pcm.shape[0]:
+        pcm = np.concatenate([pcm] * (-(-S // pcm.shape[0])))[:S]
+    skip = (rng.uniform(size=(S, T)) < 0.1).astype(np.uint8) if rng.uniform() < 0.3 else None
+    secs = (1.0 / 60.0 * (0.5 + rng.uniform(size=T))).astype(np.float32) if rng.uniform() < 0.4 else None
+    cut = int(rng.integers(1, T)) if T > 1 and rng.uniform() < 0.6 else None
+    if cut is None:
+        out = eng.process(pcm, T, hop, skip_mask=skip, frame_seconds=secs)
+        db, sil = out["db"], out["silent"]
+    else:
+        a = eng.process(pcm[:, :, : (cut - 1) * hop + N], cut, hop, skip_mask=None if skip is None else skip[:, :cut],
+                        frame_seconds=None if secs is None else secs[:cut])
+        b = eng.process(pcm[:, :, cut * hop:], T - cut, hop, skip_mask=None if skip is None else skip[:, cut:],
+                        frame_seconds=None if secs is None else secs[cut:])
+        db, sil = np.concatenate([a["db"], b["db"]], axis=1), np.concatenate([a["silent"], b["silent"]], axis=1)
+    kernel = eng.last_kernel_name()
+    for s in sorted(set([0, S // 2, S - 1])):
+        o = OracleSource(settings, channels=channels)
+        for t in range(T):
+            frames = [None if (skip is not None and skip[s, t]) else pcm[s, c, t * hop: t * hop + N] for c in range(cc)]
+            o.tick(frames, float(secs[t]) if secs is not None else 1.0 / 60.0)
+            ref = np.stack([o.decibels(d) for d in range(o.display_channels)])
+            rep = parity_report(db[s, t], ref, db_min=eng.db_min)
+            assert rep["ok"] and rep["normwise"] < 2e-6, (kernel, settings, S, T, hop, s, t, rep)
+            assert bool(sil[s, t]) == o.last_silent, (kernel, settings, S, T, hop, s, t)

@@ -32,20 +32,19 @@ constexpr size_t kStageBytes = (size_t)kN * sizeof(float); // the whole frame, T
 constexpr size_t smem_bytes() { return kBufBytes + kStageBytes + 16; }
 } // namespace par16384
 
-template<bool EXTRA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
-    stft16384_parity_kernel(const __grid_constant__ KParams p, const __grid_constant__ v3::Tw3 tw)
+// The body is instantiated once per cluster rank (r = 0: even bins, r = 1: odd bins) so that every bin index, twiddle index and
+// output address is a per-thread base + a compile-time offset: with a run-time rank ncu showed 31 % of the 23 062
+// warp-instructions per frame in IMAD / MOV / LEA / IADD3 / LOP3 / ISETP (profiles/r02_par16384.txt).
+template<bool EXTRA, int r>
+__device__ __forceinline__ void par16384_body(const KParams &p, const v3::Tw3 &tw, unsigned char *smem_raw, unsigned (*redf)[2])
 {
     using namespace wide;
     using namespace par16384;
     constexpr int B = kBins, TN = kTN, P = kP, HP = kHP, MS = kSub;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *buf = reinterpret_cast<float2 *>(smem_raw);
     const pk::c64 *stage = reinterpret_cast<const pk::c64 *>(smem_raw + kBufBytes); // frame t: pairs z[n], n < 8192
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + kBufBytes + kStageBytes);
-    __shared__ unsigned redf[2][2]; // [parity of the exchange][rank]: this rank's "all my outputs <= floor-10 dB"
     const int tid = threadIdx.x;
-    const int r = (int)cluster_ctarank(); // 0: even bins, 1: odd bins
     const int s = blockIdx.x >> 1;
     const int T = p.n_frames;
     const bool tsm = p.tsmooth != 0, gate = p.gate != 0;
@@ -360,6 +359,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
     }
     cluster_arrive(); // no CTA may exit while its peer can still address its shared memory
     cluster_wait();
+}
+
+template<bool EXTRA>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(par16384::kTN, 2)
+    stft16384_parity_kernel(const __grid_constant__ KParams p, const __grid_constant__ v3::Tw3 tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned redf[2][2]; // [parity of the exchange][rank]: this rank's "all my outputs <= floor-10 dB"
+    if(wide::cluster_ctarank() == 0)
+        par16384_body<EXTRA, 0>(p, tw, smem_raw, redf);
+    else
+        par16384_body<EXTRA, 1>(p, tw, smem_raw, redf);
 }
 
 } // namespace wf
