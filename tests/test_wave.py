@@ -139,3 +139,40 @@ def test_gpu_wave_requires_all_streams_and_reset():
     eng.reset()                              # hidden / capture-timeout branch: buffers := DB_MIN, m_last_silent := true
     out = eng.process(np.zeros((3, 1, 800), np.float32), 1, 800)
     assert out["out"].min() < -700.0
+
+
+CHUNK_CASES = WAVE_CASES + [
+    ({"width": 301, "meter_buf": 40}, 2, 97),                                       # width % 4 != 0: the scalar row path; many ticks per chunk
+    ({"width": 301, "meter_buf": 40, "channel_mode": "stereo"}, 1, 97),
+    ({"width": 1024, "meter_buf": 1000}, 1, 64),                                    # ~1.4 points per tick: chunks of 32 ticks, some ticks without points
+    ({"width": 4096, "meter_buf": 300, "channel_mode": "stereo"}, 2, 480),          # wide buffer (opt-in shared memory)
+    ({"width": 64, "meter_buf": 5, "channel_mode": "stereo", "normalize_volume": True}, 2, 2000),  # every tick replaces the whole buffer
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("settings,ch,hop", CHUNK_CASES)
+def test_gpu_wave_chunked_kernel_is_bit_identical_to_the_per_tick_kernel(settings, ch, hop, monkeypatch):
+    """wave_chunk_kernel (several ticks per barrier, sliding windows over an extended buffer) against wave_kernel (the
+    tick-by-tick restatement of src/source_generic.cpp:272-390): same rows, same silent flags, same state across calls —
+    including input built to trip the all-zero rule (|x| == 1 -> 0.0 dBFS entries followed by zeros)."""
+    from waveform_b200 import WaveEngine
+
+    S, T = 5, 90
+    pcm, rms = _case(settings, ch, hop, T, S)
+    pcm[1] = 0.0
+    pcm[2, :, : 40 * hop] = 1.0          # a buffer full of exactly 0.0 dB ...
+    pcm[2, :, 40 * hop: 70 * hop] = 0.0  # ... then zeros: the silent rule fires, repeatedly
+    pcm[3, -1] = 0.0                     # a silent second channel (the raw m_decibels[1] of the mono branch)
+    if rms is not None:
+        rms = np.repeat(rms[:, :1], T, axis=1) * np.linspace(0.5, 2.0, T, dtype=np.float32)[None, :]
+        rms[2] = 10.0 ** (settings.get("volume_target", -8.0) / 20.0)  # compensation of exactly... whatever log10f gives
+    outs = {}
+    for chunk in ("1", "0"):
+        monkeypatch.setenv("WF_WAVE_CHUNK", chunk)
+        eng = WaveEngine(settings, channels=ch, max_streams=S)
+        a = eng.process(pcm[:, :, : 13 * hop], 13, hop, input_rms=None if rms is None else rms[:, :13])
+        b = eng.process(pcm[:, :, 13 * hop:], T - 13, hop, input_rms=None if rms is None else rms[:, 13:])
+        outs[chunk] = (np.concatenate([a["out"], b["out"]], axis=1), np.concatenate([a["silent"], b["silent"]], axis=1))
+    assert np.array_equal(outs["1"][1], outs["0"][1])
+    assert np.array_equal(outs["1"][0].view(np.uint32), outs["0"][0].view(np.uint32))

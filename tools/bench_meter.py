@@ -47,4 +47,6 @@ for name, settings, ch, S, T, hop in [("waveform 800 pts / 150 ms, 2ch mixed", {
     e1.record(st); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     nbytes = S * T * (ch * hop * 4 + eng.display_channels * eng.cfg.width * 4)
-    print(f"{name:36s} {S*T/ms/1e3:8.2f} M ticks/s  {ms*1e3:8.1f} us/call  {nbytes/ms/1e6:7.1f} GB/s  frac {nbytes/ms/1e6/PEAK:.3f}")
+    kms = eng.last_kernel_ms()
+    print(f"{name:36s} {S*T/ms/1e3:8.2f} M ticks/s  {ms*1e3:8.1f} us/call  {nbytes/ms/1e6:7.1f} GB/s  frac {nbytes/ms/1e6/PEAK:.3f}"
+          f"  (kernel alone {kms*1e3:.1f} us, frac {nbytes/kms/1e6/PEAK:.3f})")

@@ -16,7 +16,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -170,6 +172,348 @@ __global__ void __launch_bounds__(256) wave_kernel(const WParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Chunked form of the same tick loop.  The per-tick kernel above has ~90 gathers in flight per CTA between barriers, so it
+// is latency-bound; here a CTA takes as many consecutive ticks as bring in at most `width` new points, gathers and converts
+// ALL of them at once (warp per 32 points, every load of the chunk in flight together), and writes each tick's row as a
+// sliding window over the extended buffer  E = [scrolling buffer at chunk start | new points of the chunk]  kept as a ring of
+// 2*width floats per channel.  The all-zero "silent" rule needs, per tick, whether the window holds any non-zero entry:
+// that is a running count  (window count) - (non-zeros leaving with this tick) + (non-zeros entering), and the per-tick
+// leaving / entering counts are accumulated by the gather warps with ballots.  A tick that does turn silent ends the chunk
+// early (the buffer becomes DB_MIN and the following ticks must see that); that is the rare path.
+//   MODE 0: one capture channel, one display channel           E0
+//   MODE 1: two capture channels mixed to one display channel  E0 (dB of the mix), E1 (RAW second channel: the reference's
+//           mono branch never converts m_decibels[1], src/source_generic.cpp:380-388 — it only takes part in the silent rule)
+//   MODE 2: two capture channels, two display channels         E0, E1 (both dB)
+//   MODE 3: one capture channel shown as two                   E0 and the raw new points N0: row 1 of a tick is the whole-buffer
+//           copy taken BEFORE the tick's conversion (:368-369), i.e. older points in dB, the tick's own points raw
+constexpr int WCH_KMAX = 32; // ticks per chunk: one lane each in the gather phase
+constexpr int WCH_U = 4;     // items (32 points) a warp has in flight
+
+struct WChunkTick {
+    int leave0, in_db0, in_raw0, leave1, in1, in_raw1;
+};
+
+__device__ __forceinline__ int wrap2(int x, int cap) { return x - ((x >= cap) ? cap : 0); }
+
+template<int MODE>
+__global__ void __launch_bounds__(256, 5) wave_chunk_kernel(const WParams p)
+{
+    extern __shared__ float wsm[];
+    __shared__ WChunkTick s_cnt[2][WCH_KMAX];
+    __shared__ int s_off[WCH_KMAX + 1];
+    constexpr bool TWO = (MODE == 1 || MODE == 2); // second capture channel present
+    constexpr int DCH = (MODE >= 2) ? 2 : 1;
+    constexpr int nt = 256, nwarps = nt / 32; // the launch uses exactly 256 threads
+    const int W = p.width, CAP = 2 * W, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    float *E0 = wsm;
+    float *E1 = wsm + CAP;                               // MODE 1, 2
+    float *N0 = wsm + CAP;                               // MODE 3 (raw new points of the chunk, chunk-relative index)
+    const bool vec = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    for(int s = blockIdx.x; s < p.n_streams; s += gridDim.x)
+    {
+        const float *pcm0 = p.pcm + (size_t)s * p.stream_stride;
+        const float *pcm1 = pcm0 + p.channel_stride;
+        float *st0 = p.state + (size_t)s * 2 * W, *st1 = st0 + W;
+        int wc0 = 0, wc1 = 0; // non-zero entries in the current window of E0 / E1
+        {
+            int c0 = 0, c1 = 0;
+            for(int i = tid; i < W; i += nt)
+            {
+                const float a = st0[i];
+                E0[i] = a;
+                c0 += (a != 0.0f);
+                if(TWO)
+                {
+                    const float b = st1[i];
+                    E1[i] = b;
+                    c1 += (b != 0.0f);
+                }
+            }
+            if(tid < 2 * WCH_KMAX)
+                reinterpret_cast<WChunkTick *>(s_cnt)[tid] = WChunkTick{0, 0, 0, 0, 0, 0};
+            // block sums (once per stream and call)
+            for(int o = 16; o > 0; o >>= 1)
+            {
+                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            }
+            __shared__ int s_red[2][8];
+            if(lane == 0)
+            {
+                s_red[0][warp] = c0;
+                s_red[1][warp] = c1;
+            }
+            __syncthreads();
+            for(int w = 0; w < nwarps; ++w)
+            {
+                wc0 += s_red[0][w];
+                wc1 += s_red[1][w];
+            }
+        }
+        int base = 0, par = 0;
+        bool last_silent = p.flags[s] != 0;
+        int t = 0;
+        while(t < p.n_ticks)
+        {
+            // the chunk: ticks [t, t+K) with at most W new points in total (the first tick is always taken: a tick never
+            // brings more than W points)
+            const int obase = __ldg(p.off + t);
+            int K = 0, C = 0;
+            while(t + K < p.n_ticks && K < WCH_KMAX)
+            {
+                const int c = __ldg(p.off + t + K + 1) - obase - C;
+                if(K > 0 && C + c > W)
+                    break;
+                C += c;
+                ++K;
+            }
+            // phase 1: gather + convert, one warp per item of 32 points, WCH_U items per pass so that a warp has that many
+            // dependent src -> sample load chains in flight; per-tick leaving / entering non-zero counts by ballot.
+            // Lane l holds tick l's offsets; an item number maps to its tick through a ballot over the running item ends.
+            {
+                int oj_l = 0, c_l = 0;
+                if(lane < K)
+                {
+                    oj_l = __ldg(p.off + t + lane) - obase;
+                    c_l = __ldg(p.off + t + lane + 1) - obase - oj_l;
+                }
+                const int nb_l = (c_l + 31) >> 5;
+                int end_l = nb_l;
+#pragma unroll
+                for(int o = 1; o < 32; o <<= 1)
+                {
+                    const int v = __shfl_up_sync(0xffffffffu, end_l, o);
+                    end_l += (lane >= o) ? v : 0;
+                }
+                const int total = __shfl_sync(0xffffffffu, end_l, 31);
+                if(warp == 0)
+                {
+                    if(lane < K)
+                        s_off[lane + 1] = oj_l + c_l;
+                    if(lane == 0)
+                        s_off[0] = 0;
+                    s_cnt[par ^ 1][lane] = WChunkTick{0, 0, 0, 0, 0, 0}; // the next chunk's counters (last read two barriers ago)
+                }
+                for(int g0 = warp; g0 < total; g0 += nwarps * WCH_U)
+                {
+                    int jj[WCH_U], rel[WCH_U], q[WCH_U];
+                    float ra[WCH_U], rb[WCH_U];
+#pragma unroll
+                    for(int u = 0; u < WCH_U; ++u)
+                    {
+                        const int g = g0 + u * nwarps;
+                        const int j = min(__popc(__ballot_sync(0xffffffffu, lane < K && end_l <= g)), K - 1);
+                        const int oj = __shfl_sync(0xffffffffu, oj_l, j), c = __shfl_sync(0xffffffffu, c_l, j);
+                        const int first = __shfl_sync(0xffffffffu, end_l - nb_l, j);
+                        const int i = (g - first) * 32 + lane;
+                        const bool act = (g < total) && (i < c);
+                        jj[u] = (g < total) ? j : -1;
+                        rel[u] = act ? (oj + i) : -1;
+                        q[u] = act ? __ldg(p.src + obase + oj + i) : -1;
+                    }
+#pragma unroll
+                    for(int u = 0; u < WCH_U; ++u)
+                    {
+                        ra[u] = (q[u] >= 0) ? __ldg(pcm0 + q[u]) : 0.0f;
+                        rb[u] = (TWO && q[u] >= 0) ? __ldg(pcm1 + q[u]) : 0.0f;
+                    }
+#pragma unroll
+                    for(int u = 0; u < WCH_U; ++u)
+                    {
+                        if(jj[u] < 0)
+                            continue; // warp-uniform
+                        const bool act = rel[u] >= 0;
+                        float vc = 0.0f;
+                        if(p.normalize)
+                        {
+                            const float rms = (p.input_rms != nullptr) ? p.input_rms[(size_t)s * p.n_ticks + t + jj[u]] : 0.0f;
+                            vc = fminf(p.vol_target - dbfs_dev(rms, p.db_min), p.max_gain);
+                        }
+                        const int pl = wrap2(base + max(rel[u], 0), CAP), pn = wrap2(base + W + max(rel[u], 0), CAP);
+                        const bool l0 = act && (E0[pl] != 0.0f);
+                        const bool l1 = TWO && act && (E1[pl] != 0.0f);
+                        float a, b1 = 0.0f;
+                        if(MODE == 1)
+                            a = dbfs_dev((fabsf(ra[u]) + fabsf(rb[u])) * 0.5f, p.db_min);
+                        else
+                            a = dbfs_dev(fabsf(ra[u]), p.db_min);
+                        if(p.normalize)
+                            a += vc;
+                        if(MODE == 2)
+                        {
+                            b1 = dbfs_dev(fabsf(rb[u]), p.db_min);
+                            if(p.normalize)
+                                b1 += vc;
+                        }
+                        else if(MODE == 1)
+                            b1 = rb[u];
+                        if(act)
+                        {
+                            E0[pn] = a;
+                            if(TWO)
+                                E1[pn] = b1;
+                            if(MODE == 3)
+                                N0[rel[u]] = ra[u];
+                        }
+                        const unsigned m_l0 = __ballot_sync(0xffffffffu, l0), m_a = __ballot_sync(0xffffffffu, act && a != 0.0f),
+                                       m_ra = __ballot_sync(0xffffffffu, act && ra[u] != 0.0f);
+                        unsigned m_l1 = 0, m_b = 0, m_rb = 0;
+                        if(TWO)
+                        {
+                            m_l1 = __ballot_sync(0xffffffffu, l1);
+                            m_b = __ballot_sync(0xffffffffu, act && b1 != 0.0f);
+                            m_rb = __ballot_sync(0xffffffffu, act && rb[u] != 0.0f);
+                        }
+                        if(lane == 0)
+                        {
+                            WChunkTick *ct = &s_cnt[par][jj[u]];
+                            if(m_l0)
+                                atomicAdd(&ct->leave0, __popc(m_l0));
+                            if(m_a)
+                                atomicAdd(&ct->in_db0, __popc(m_a));
+                            if(m_ra)
+                                atomicAdd(&ct->in_raw0, __popc(m_ra));
+                            if(TWO)
+                            {
+                                if(m_l1)
+                                    atomicAdd(&ct->leave1, __popc(m_l1));
+                                if(m_b)
+                                    atomicAdd(&ct->in1, __popc(m_b));
+                                if(m_rb)
+                                    atomicAdd(&ct->in_raw1, __popc(m_rb));
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // phase 2: the silent rule per tick (:341-356; with m_last_silent assigned on every path it reduces to "no
+            // channel has a non-zero entry"), uniform over the CTA
+            int Kc = K;
+            bool hit = false;
+            for(int j = 0; j < K; ++j)
+            {
+                const WChunkTick ct = s_cnt[par][j];
+                wc0 -= ct.leave0;
+                bool any = (wc0 > 0) || (ct.in_raw0 > 0);
+                if(MODE == 2)
+                {
+                    wc1 -= ct.leave1;
+                    any = any || (wc1 > 0) || (ct.in_raw1 > 0);
+                }
+                if(MODE == 1)
+                {
+                    wc1 += ct.in1 - ct.leave1; // raw buffer: the tick's own points are part of what is tested
+                    any = any || (wc1 > 0);
+                }
+                if(!any)
+                {
+                    Kc = j + 1;
+                    hit = true;
+                    break;
+                }
+                wc0 += ct.in_db0;
+                if(MODE == 2)
+                    wc1 += ct.in1;
+            }
+            // rows of ticks [t, t+Kc): windows of E in time order
+            {
+                const bool wr_state1 = (MODE == 3) && (t + Kc == p.n_ticks);
+                if(vec)
+                {
+                    const int W4 = W >> 2, per = DCH * W4, total = Kc * per;
+                    for(int it = tid; it < total; it += nt)
+                    {
+                        const int j = it / per, r = it - j * per, d = (DCH == 2) ? (r >= W4) : 0, i = (r - d * W4) * 4;
+                        const bool sil = hit && (j == Kc - 1);
+                        float4 v;
+                        if(sil)
+                            v = make_float4(p.db_min, p.db_min, p.db_min, p.db_min);
+                        else
+                        {
+                            const int o1 = s_off[j + 1];
+                            float e[4];
+#pragma unroll
+                            for(int k = 0; k < 4; ++k)
+                            {
+                                const int rel = o1 + i + k;
+                                if(MODE == 3 && d == 1)
+                                    e[k] = (rel < W + s_off[j]) ? E0[wrap2(base + rel, CAP)] : N0[rel - W];
+                                else
+                                    e[k] = ((d == 0) ? E0 : E1)[wrap2(base + rel, CAP)];
+                            }
+                            v = make_float4(e[0], e[1], e[2], e[3]);
+                        }
+                        __stcs(reinterpret_cast<float4 *>(p.out + (((size_t)s * p.n_ticks + t + j) * DCH + d) * W + i), v);
+                        if(wr_state1 && d == 1 && j == Kc - 1)
+                            *reinterpret_cast<float4 *>(st1 + i) = v;
+                    }
+                }
+                else
+                {
+                    const int per = DCH * W, total = Kc * per;
+                    for(int it = tid; it < total; it += nt)
+                    {
+                        const int j = it / per, r = it - j * per, d = (DCH == 2) ? (r >= W) : 0, i = r - d * W;
+                        const bool sil = hit && (j == Kc - 1);
+                        float v = p.db_min;
+                        if(!sil)
+                        {
+                            const int rel = s_off[j + 1] + i;
+                            if(MODE == 3 && d == 1)
+                                v = (rel < W + s_off[j]) ? E0[wrap2(base + rel, CAP)] : N0[rel - W];
+                            else
+                                v = ((d == 0) ? E0 : E1)[wrap2(base + rel, CAP)];
+                        }
+                        __stcs(p.out + (((size_t)s * p.n_ticks + t + j) * DCH + d) * W + i, v);
+                        if(wr_state1 && d == 1 && j == Kc - 1)
+                            st1[i] = v;
+                    }
+                }
+                if(p.out_silent != nullptr && tid < Kc)
+                    p.out_silent[(size_t)s * p.n_ticks + t + tid] = (hit && tid == Kc - 1) ? 1 : 0;
+            }
+            last_silent = hit;
+            if(hit)
+            {
+                // :360-366: the display channels become DB_MIN; the ticks after it start from that buffer
+                __syncthreads();
+                base = wrap2(base + s_off[Kc], CAP);
+                for(int i = tid; i < W; i += nt)
+                {
+                    E0[wrap2(base + i, CAP)] = p.db_min;
+                    if(MODE == 2)
+                        E1[wrap2(base + i, CAP)] = p.db_min;
+                }
+                wc0 = W;
+                if(MODE == 2)
+                    wc1 = W;
+                if(tid < WCH_KMAX)
+                    s_cnt[par][tid] = WChunkTick{0, 0, 0, 0, 0, 0};
+                t += Kc;
+            }
+            else
+            {
+                base = wrap2(base + C, CAP);
+                t += K;
+                par ^= 1;
+            }
+            __syncthreads();
+        }
+        for(int i = tid; i < W; i += nt)
+        {
+            st0[i] = E0[wrap2(base + i, CAP)];
+            if(TWO)
+                st1[i] = E1[wrap2(base + i, CAP)];
+        }
+        if(tid == 0)
+            p.flags[s] = last_silent ? 1 : 0;
+        __syncthreads();
+    }
+}
+
 __global__ void wave_fill_kernel(float *q, long long n, float v)
 {
     for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -191,8 +535,21 @@ __global__ void wave_reset_kernel(float *state, unsigned char *flags, int n_stre
     }
 }
 
-uint64_t frames_to_ns(uint64_t sr, uint64_t frames) { return (uint64_t)(((unsigned __int128)frames * 1000000000ull) / sr); }
-uint64_t ns_to_frames(uint64_t sr, uint64_t ns) { return (uint64_t)(((unsigned __int128)ns * sr) / 1000000000ull); }
+// util.hpp's audio_frames_to_ns / ns_to_audio_frames (128-bit multiply-divide).  The 64-bit form is the same quotient
+// whenever the product fits, which it does for everything but multi-day spans; the 128-bit division costs ~50 ns and the
+// plan evaluates one per point.
+uint64_t frames_to_ns(uint64_t sr, uint64_t frames)
+{
+    if(frames <= UINT64_MAX / 1000000000ull)
+        return (frames * 1000000000ull) / sr;
+    return (uint64_t)(((unsigned __int128)frames * 1000000000ull) / sr);
+}
+uint64_t ns_to_frames(uint64_t sr, uint64_t ns)
+{
+    if(ns <= UINT64_MAX / sr)
+        return (ns * sr) / 1000000000ull;
+    return (uint64_t)(((unsigned __int128)ns * sr) / 1000000000ull);
+}
 
 } // namespace
 
@@ -216,6 +573,18 @@ struct wf_wave {
     float *s_pcm = nullptr, *s_out = nullptr, *s_rms = nullptr;
     unsigned char *s_silent = nullptr;
     size_t src_cap = 0, off_cap = 0, pcm_cap = 0, out_cap = 0, rms_cap = 0, silent_cap = 0;
+    struct PlanSlot {
+        int *h = nullptr; // pinned: off[] then src[]
+        size_t cap = 0;
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    static constexpr int kSlots = 4;
+    PlanSlot slots[kSlots];
+    int slot_next = 0;
+    cudaStream_t last_stream = nullptr;
+    bool chunked = true;  // wave_chunk_kernel (WF_WAVE_CHUNK=0: the per-tick kernel, kept for A/B and bit-identity tests)
+    int chunk_mode = 0, chunk_floats = 0, chunk_per_sm = 8;
 };
 
 namespace {
@@ -394,6 +763,34 @@ int wf_wave_create(const wf_wave_config *cfg, wf_wave **out)
     w->sm_count = prop.multiProcessorCount;
     if(2 * (size_t)cfg->width * sizeof(float) > 48 * 1024) // widths above 6144: both scrolling rings exceed the default 48 KB
         WFW_C(cudaFuncSetAttribute(wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (size_t)cfg->width * sizeof(float))));
+    {
+        const char *e = getenv("WF_WAVE_CHUNK");
+        w->chunked = !(e && e[0] == '0');
+        const bool two = cfg->capture_channels > 1;
+        w->chunk_mode = cfg->stereo ? (two ? 2 : 3) : (two ? 1 : 0);
+        static const int mult[4] = {2, 4, 4, 3};
+        w->chunk_floats = mult[w->chunk_mode] * cfg->width;
+        const int bytes = w->chunk_floats * (int)sizeof(float);
+        if(bytes > 48 * 1024)
+        {
+            switch(w->chunk_mode)
+            {
+            case 0: WFW_C(cudaFuncSetAttribute(wave_chunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+            case 1: WFW_C(cudaFuncSetAttribute(wave_chunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+            case 2: WFW_C(cudaFuncSetAttribute(wave_chunk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+            default: WFW_C(cudaFuncSetAttribute(wave_chunk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); break;
+            }
+        }
+        int per_sm = 0;
+        switch(w->chunk_mode)
+        {
+        case 0: WFW_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_chunk_kernel<0>, 256, (size_t)bytes)); break;
+        case 1: WFW_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_chunk_kernel<1>, 256, (size_t)bytes)); break;
+        case 2: WFW_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_chunk_kernel<2>, 256, (size_t)bytes)); break;
+        default: WFW_C(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wave_chunk_kernel<3>, 256, (size_t)bytes)); break;
+        }
+        w->chunk_per_sm = std::max(1, per_sm); // one resident wave: streams are equal work, a partial second wave is a tail
+    }
     WFW_C(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     WFW_C(cudaEventCreate(&w->ev0));
     WFW_C(cudaEventCreate(&w->ev1));
@@ -418,11 +815,20 @@ void wf_wave_destroy(wf_wave *w)
     {
         cudaSetDevice(w->device);
         cudaStreamSynchronize(w->stream);
+        if(w->last_stream && w->last_stream != w->stream)
+            cudaStreamSynchronize(w->last_stream);
     }
     void *ptrs[] = {w->d_state, w->d_flags, w->d_src, w->d_off, w->s_pcm, w->s_out, w->s_rms, w->s_silent};
     for(void *q : ptrs)
         if(q)
             cudaFree(q);
+    for(auto &ps : w->slots)
+    {
+        if(ps.h)
+            cudaFreeHost(ps.h);
+        if(ps.done)
+            cudaEventDestroy(ps.done);
+    }
     if(w->ev0)
         cudaEventDestroy(w->ev0);
     if(w->ev1)
@@ -464,10 +870,37 @@ int wf_wave_process_async(wf_wave *w, const wf_wave_batch *b, void *cuda_stream)
         return rc;
     if((rc = wensure(w, &w->d_off, &w->off_cap, off.size())))
         return rc;
-    if(!src.empty())
-        WFW_CUDA(w, cudaMemcpyAsync(w->d_src, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    WFW_CUDA(w, cudaMemcpyAsync(w->d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    WFW_CUDA(w, cudaStreamSynchronize(st)); // the plan vectors are stack-owned: the copies must finish before they go away
+    {
+        // the plan goes through one of a few pinned slots, so a call neither waits for the previous kernel nor leaves the
+        // device reading a vector that is about to go away; a slot is reused only after its copy has completed
+        wf_wave::PlanSlot &ps = w->slots[w->slot_next];
+        w->slot_next = (w->slot_next + 1) % wf_wave::kSlots;
+        if(ps.used)
+            WFW_CUDA(w, cudaEventSynchronize(ps.done));
+        const size_t need = src.size() + off.size();
+        if(need > ps.cap)
+        {
+            if(ps.h)
+                cudaFreeHost(ps.h);
+            ps.h = nullptr;
+            ps.cap = 0;
+            WFW_CUDA(w, cudaMallocHost((void **)&ps.h, need * sizeof(int)));
+            ps.cap = need;
+        }
+        if(!ps.done)
+            WFW_CUDA(w, cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+        memcpy(ps.h, off.data(), off.size() * sizeof(int));
+        if(!src.empty())
+            memcpy(ps.h + off.size(), src.data(), src.size() * sizeof(int));
+        if(w->last_stream != nullptr && w->last_stream != st)
+            WFW_CUDA(w, cudaStreamSynchronize(w->last_stream)); // d_src / d_off may still be read by a call on another stream
+        w->last_stream = st;
+        WFW_CUDA(w, cudaMemcpyAsync(w->d_off, ps.h, off.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        if(!src.empty())
+            WFW_CUDA(w, cudaMemcpyAsync(w->d_src, ps.h + off.size(), src.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        WFW_CUDA(w, cudaEventRecord(ps.done, st));
+        ps.used = true;
+    }
 
     const bool dev_ptrs = w_is_device_ptr(b->pcm);
     const float *d_pcm = b->pcm, *d_rms = b->input_rms;
@@ -521,8 +954,20 @@ int wf_wave_process_async(wf_wave *w, const wf_wave_batch *b, void *cuda_stream)
     p.max_gain = w->cfg.max_gain;
     p.db_min = w->db_min;
     WFW_CUDA(w, cudaEventRecord(w->ev0, st));
-    const int grid = (int)std::min<size_t>(S, (size_t)w->sm_count * 8);
-    wave_kernel<<<grid, 256, 2 * (size_t)W * sizeof(float), st>>>(p);
+    const int grid = (int)std::min<size_t>(S, (size_t)w->sm_count * (w->chunked ? w->chunk_per_sm : 8));
+    if(w->chunked)
+    {
+        const size_t smem = (size_t)w->chunk_floats * sizeof(float);
+        switch(w->chunk_mode)
+        {
+        case 0: wave_chunk_kernel<0><<<grid, 256, smem, st>>>(p); break;
+        case 1: wave_chunk_kernel<1><<<grid, 256, smem, st>>>(p); break;
+        case 2: wave_chunk_kernel<2><<<grid, 256, smem, st>>>(p); break;
+        default: wave_chunk_kernel<3><<<grid, 256, smem, st>>>(p); break;
+        }
+    }
+    else
+        wave_kernel<<<grid, 256, 2 * (size_t)W * sizeof(float), st>>>(p);
     WFW_CUDA(w, cudaGetLastError());
     w->launches++;
     WFW_CUDA(w, cudaEventRecord(w->ev1, st));
