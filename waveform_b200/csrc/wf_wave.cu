@@ -259,26 +259,23 @@ __global__ void __launch_bounds__(256, 5) wave_chunk_kernel(const WParams p)
         {
             // the chunk: ticks [t, t+K) with at most W new points in total (the first tick is always taken: a tick never
             // brings more than W points)
+            // (lane l looks at tick t+l: the cumulative point counts are monotone, so the chunk is a ballot)
             const int obase = __ldg(p.off + t);
-            int K = 0, C = 0;
-            while(t + K < p.n_ticks && K < WCH_KMAX)
-            {
-                const int c = __ldg(p.off + t + K + 1) - obase - C;
-                if(K > 0 && C + c > W)
-                    break;
-                C += c;
-                ++K;
-            }
+            const bool tick_l = (t + lane) < p.n_ticks;
+            const int cum_l = tick_l ? (__ldg(p.off + t + lane + 1) - obase) : 0x3fffffff;
+            const int K = max(1, __popc(__ballot_sync(0xffffffffu, tick_l && cum_l <= W)));
+            const int C = __shfl_sync(0xffffffffu, cum_l, K - 1);
             // phase 1: gather + convert, one warp per item of 32 points, WCH_U items per pass so that a warp has that many
             // dependent src -> sample load chains in flight; per-tick leaving / entering non-zero counts by ballot.
             // Lane l holds tick l's offsets; an item number maps to its tick through a ballot over the running item ends.
             {
-                int oj_l = 0, c_l = 0;
+                int oj_l = __shfl_up_sync(0xffffffffu, cum_l, 1), c_l = 0;
+                if(lane == 0)
+                    oj_l = 0;
                 if(lane < K)
-                {
-                    oj_l = __ldg(p.off + t + lane) - obase;
-                    c_l = __ldg(p.off + t + lane + 1) - obase - oj_l;
-                }
+                    c_l = cum_l - oj_l;
+                else
+                    oj_l = 0;
                 const int nb_l = (c_l + 31) >> 5;
                 int end_l = nb_l;
 #pragma unroll
@@ -391,64 +388,95 @@ __global__ void __launch_bounds__(256, 5) wave_chunk_kernel(const WParams p)
             __syncthreads();
             // phase 2: the silent rule per tick (:341-356; with m_last_silent assigned on every path it reduces to "no
             // channel has a non-zero entry"), uniform over the CTA
+            // Lane l evaluates tick l: the window count before its test is the count at chunk start plus the (entering -
+            // leaving) sums of the ticks before it, minus what leaves with it.
             int Kc = K;
             bool hit = false;
-            for(int j = 0; j < K; ++j)
             {
-                const WChunkTick ct = s_cnt[par][j];
-                wc0 -= ct.leave0;
-                bool any = (wc0 > 0) || (ct.in_raw0 > 0);
-                if(MODE == 2)
+                WChunkTick ct{0, 0, 0, 0, 0, 0};
+                if(lane < K)
+                    ct = s_cnt[par][lane];
+                int s0 = ct.in_db0 - ct.leave0, s1 = ct.in1 - ct.leave1;
+#pragma unroll
+                for(int o = 1; o < 32; o <<= 1)
                 {
-                    wc1 -= ct.leave1;
-                    any = any || (wc1 > 0) || (ct.in_raw1 > 0);
+                    const int v0 = __shfl_up_sync(0xffffffffu, s0, o), v1 = __shfl_up_sync(0xffffffffu, s1, o);
+                    s0 += (lane >= o) ? v0 : 0;
+                    if(TWO)
+                        s1 += (lane >= o) ? v1 : 0;
                 }
+                bool any = (wc0 + s0 - ct.in_db0 > 0) || (ct.in_raw0 > 0);
+                if(MODE == 2)
+                    any = any || (wc1 + s1 - ct.in1 > 0) || (ct.in_raw1 > 0);
                 if(MODE == 1)
+                    any = any || (wc1 + s1 > 0); // raw buffer: the tick's own points are part of what is tested
+                const unsigned silent_mask = __ballot_sync(0xffffffffu, lane < K && !any);
+                if(silent_mask != 0)
                 {
-                    wc1 += ct.in1 - ct.leave1; // raw buffer: the tick's own points are part of what is tested
-                    any = any || (wc1 > 0);
-                }
-                if(!any)
-                {
-                    Kc = j + 1;
                     hit = true;
-                    break;
+                    Kc = __ffs(silent_mask);
                 }
-                wc0 += ct.in_db0;
-                if(MODE == 2)
-                    wc1 += ct.in1;
+                // counts after the last processed tick (the DB_MIN fill below overrides the display channels after a hit)
+                wc0 += __shfl_sync(0xffffffffu, s0, Kc - 1);
+                if(TWO)
+                    wc1 += __shfl_sync(0xffffffffu, s1, Kc - 1);
             }
             // rows of ticks [t, t+Kc): windows of E in time order
             {
                 const bool wr_state1 = (MODE == 3) && (t + Kc == p.n_ticks);
                 if(vec)
                 {
-                    const int W4 = W >> 2, per = DCH * W4, total = Kc * per;
+                    // one float4 of a row per thread and step; the silent row (at most the last one) is a constant
+                    const int W4 = W >> 2, per = DCH * W4, rows = Kc - (hit ? 1 : 0), total = rows * per;
+                    const unsigned magic = 0xffffffffu / (unsigned)per + 1u; // it / per == umulhi(it, magic) for it * per < 2^32
                     for(int it = tid; it < total; it += nt)
                     {
-                        const int j = it / per, r = it - j * per, d = (DCH == 2) ? (r >= W4) : 0, i = (r - d * W4) * 4;
-                        const bool sil = hit && (j == Kc - 1);
-                        float4 v;
-                        if(sil)
-                            v = make_float4(p.db_min, p.db_min, p.db_min, p.db_min);
-                        else
+                        const int j = (int)__umulhi((unsigned)it, magic), r = it - j * per, d = (DCH == 2) ? (r >= W4) : 0,
+                                  i = (r - d * W4) * 4;
+                        const int o1 = s_off[j + 1];
+                        float e[4];
+                        if(MODE == 3 && d == 1)
                         {
-                            const int o1 = s_off[j + 1];
-                            float e[4];
+                            const int lim = W + s_off[j];
 #pragma unroll
                             for(int k = 0; k < 4; ++k)
                             {
                                 const int rel = o1 + i + k;
-                                if(MODE == 3 && d == 1)
-                                    e[k] = (rel < W + s_off[j]) ? E0[wrap2(base + rel, CAP)] : N0[rel - W];
-                                else
-                                    e[k] = ((d == 0) ? E0 : E1)[wrap2(base + rel, CAP)];
+                                e[k] = (rel < lim) ? E0[wrap2(base + rel, CAP)] : N0[rel - W];
                             }
-                            v = make_float4(e[0], e[1], e[2], e[3]);
                         }
+                        else
+                        {
+                            const float *Ed = (DCH == 2 && d == 1) ? E1 : E0;
+                            const int start = wrap2(base + o1 + i, CAP);
+                            if(start + 3 < CAP)
+                            {
+#pragma unroll
+                                for(int k = 0; k < 4; ++k)
+                                    e[k] = Ed[start + k];
+                            }
+                            else
+                            {
+#pragma unroll
+                                for(int k = 0; k < 4; ++k)
+                                    e[k] = Ed[wrap2(start + k, CAP)];
+                            }
+                        }
+                        const float4 v = make_float4(e[0], e[1], e[2], e[3]);
                         __stcs(reinterpret_cast<float4 *>(p.out + (((size_t)s * p.n_ticks + t + j) * DCH + d) * W + i), v);
                         if(wr_state1 && d == 1 && j == Kc - 1)
                             *reinterpret_cast<float4 *>(st1 + i) = v;
+                    }
+                    if(hit)
+                    {
+                        const float4 v = make_float4(p.db_min, p.db_min, p.db_min, p.db_min);
+                        float4 *orow = reinterpret_cast<float4 *>(p.out + ((size_t)s * p.n_ticks + t + Kc - 1) * DCH * W);
+                        for(int it = tid; it < per; it += nt)
+                        {
+                            __stcs(orow + it, v);
+                            if(wr_state1 && it >= W4)
+                                reinterpret_cast<float4 *>(st1)[it - W4] = v;
+                        }
                     }
                 }
                 else
