@@ -20,7 +20,8 @@ CASES = [({"fft_size": 2048}, 1, 20, 3, 1, False),
          ({"fft_size": 800}, 1, 40, 5, 1, False),
          ({"fft_size": 1920, "slope": 0.5, "fast_peaks": True}, 1, 9, 4, 2, False),
          ({"fft_size": 1456}, 1, 5, 3, 1, False)]
-for s, ch, S, T, hopdiv, pts in CASES:
+ONLY_NEXT = "--next-rows" in sys.argv   # meter / feed / waveform only (short enough for racecheck)
+for s, ch, S, T, hopdiv, pts in ([] if ONLY_NEXT else CASES):
     e = Engine(s, channels=ch, max_streams=S); N = e.fft_size; hop = N // hopdiv
     x = synth_pcm(S, e.capture_channels, (T - 1) * hop + N); x[0, :, :] = 0
     if T > 20:
@@ -43,9 +44,16 @@ for mode, st in ((None, {"meter_buf": 20, "rms_mode": True}), (None, {"meter_buf
         a = m.process(x[:, :, : 4 * hop], 4, hop); b = m.process(torch.from_numpy(x[:, :, 4 * hop:]).cuda(), 5, hop)
         torch.cuda.synchronize()
         print("meter", mode, hop, "ok", flush=True)
-for st, ch in (({"width": 300, "meter_buf": 50, "channel_mode": "stereo"}, 2), ({"width": 200, "meter_buf": 10}, 1)):
+# waveform mode: the four channel layouts of the chunked kernel, many ticks per chunk (hop 97), a tick that replaces the whole
+# buffer (hop 2000 at 64 points / 5 ms), and input that trips the silent rule (|x| = 1 for a full buffer, then zeros)
+for st, ch, hop in (({"width": 300, "meter_buf": 50, "channel_mode": "stereo"}, 2, 800), ({"width": 200, "meter_buf": 10}, 1, 800),
+                    ({"width": 301, "meter_buf": 40}, 2, 97), ({"width": 301, "meter_buf": 40, "channel_mode": "stereo"}, 1, 97),
+                    ({"width": 64, "meter_buf": 5, "channel_mode": "stereo"}, 2, 2000)):
     w = WaveEngine(st, channels=ch, max_streams=3)
-    x = synth_pcm(3, ch, 9 * 800)
-    a = w.process(x[:, :, : 4 * 800], 4, 800); b = w.process(torch.from_numpy(x[:, :, 4 * 800:]).cuda(), 5, 800)
+    T = 40
+    x = synth_pcm(3, ch, T * hop)
+    x[1, :, : 25 * hop] = 1.0
+    x[1, :, 25 * hop:] = 0.0
+    a = w.process(x[:, :, : 4 * hop], 4, hop); b = w.process(torch.from_numpy(x[:, :, 4 * hop:]).cuda(), T - 4, hop)
     torch.cuda.synchronize()
-    print("wave", st["width"], "ok", flush=True)
+    print("wave", st["width"], ch, hop, "ok silent ticks:", int(b["silent"].sum()), flush=True)

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
     __syncthreads();
     for(int i = threadIdx.x; i < pc * nb; i += blockDim.x) // the ring's partials for the next call
         p.part_out[(size_t)s * pc * nb + i] = part[(i / nb) * NB + T + (i % nb)];
-    // window of tick t = blocks [t+1, t+1+nb)
+    // window of tick t = blocks [t+1, t+1+nb); the RMS of the window (:243) is per tick, so it is taken here, in parallel
     for(int idx = threadIdx.x; idx < T * pc; idx += blockDim.x)
     {
         const int t = idx / pc, c = idx - t * pc;
@@ -379,6 +379,8 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
         float acc = q[0];
         for(int i = 1; i < nb; ++i)
             acc = combine<MODE>(acc, q[i]);
+        if(MODE == WF_METER_RMS)
+            acc = __fsqrt_rn(__fdiv_rn(acc, (float)W)); // :243
         raw[idx] = acc;
     }
     __syncthreads();
@@ -389,41 +391,49 @@ __global__ void __launch_bounds__(256) meter_fused_kernel(const MParams p)
                 p.out_lin[(size_t)s * T + t] = __fsqrt_rn(__fdiv_rn(raw[t], (float)W)); // src/source_generic.cpp:402
         return;
     }
-    if(warp == 0)
+    // per-stream recurrence (src/source_generic.cpp:232-269).  Only the temporal smoothing is sequential (two dependent
+    // operations per tick): lane c < cc of warp 0 walks its channel and leaves the smoothed value in place; dBFS, the silent
+    // rule and the stores are per tick again and run on all threads.  (A CTA stays resident until its slowest warp is done:
+    // with the whole tail on one lane — sqrt, divide, log10f and a ballot per tick — 30 % of a CTA's life had 7 of 8 warps idle.)
+    if(warp == 0 && lane < cc)
     {
-        // per-stream recurrence (src/source_generic.cpp:232-269): lane c < cc walks its channel, the silent rule needs both
-        const int c = (lane < cc) ? lane : 0;
+        const int c = lane;
         float buf = p.buf[2 * s + c];
-        bool last_silent = p.flags[s] != 0;
-        for(int t = 0; t < T; ++t)
+        if(p.tsmooth)
         {
-            float out = raw[t * pc + c];
-            if(MODE == WF_METER_RMS)
-                out = __fsqrt_rn(__fdiv_rn(out, (float)W)); // :243
-            if(p.tsmooth)
+            for(int t = 0; t < T; ++t)
             {
+                float out = raw[t * pc + c];
                 if(!p.fast_peaks || (out <= buf))
                     out = __fadd_rn(__fmul_rn(p.g, buf), __fmul_rn(p.g2, out)); // :255-256
+                buf = out;
+                raw[t * pc + c] = out;
             }
-            buf = out;
-            const float val = (out > 0.0f) ? 20.0f * log10f(out) : p.db_min; // dbfs, src/source.hpp:293-299
-            const unsigned below = __ballot_sync(0xffffffffu, (lane < cc) && (val < p.floor_m10));
-            last_silent = __popc(below) >= cc; // :264-269
-            if(lane < cc)
-            {
-                const size_t o = ((size_t)s * T + t) * cc + c;
-                if(p.out_db)
-                    p.out_db[o] = val;
-                if(p.out_lin)
-                    p.out_lin[o] = out;
-            }
-            if(p.out_silent && lane == 0)
-                p.out_silent[(size_t)s * T + t] = last_silent ? 1 : 0;
         }
-        if(lane < cc)
-            p.buf[2 * s + c] = buf;
-        if(lane == 0)
-            p.flags[s] = last_silent ? 1 : 0;
+        else
+            buf = raw[(T - 1) * pc + c];
+        p.buf[2 * s + c] = buf;
+    }
+    __syncthreads();
+    for(int t = threadIdx.x; t < T; t += blockDim.x)
+    {
+        int below = 0;
+        for(int c = 0; c < cc; ++c)
+        {
+            const float out = raw[t * pc + c];
+            const float val = (out > 0.0f) ? 20.0f * log10f(out) : p.db_min; // dbfs, src/source.hpp:293-299
+            below += (val < p.floor_m10) ? 1 : 0;
+            const size_t o = ((size_t)s * T + t) * cc + c;
+            if(p.out_db)
+                p.out_db[o] = val;
+            if(p.out_lin)
+                p.out_lin[o] = out;
+        }
+        const bool silent = below >= cc; // :264-269
+        if(p.out_silent)
+            p.out_silent[(size_t)s * T + t] = silent ? 1 : 0;
+        if(t == T - 1)
+            p.flags[s] = silent ? 1 : 0;
     }
 }
 
