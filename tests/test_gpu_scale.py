@@ -106,6 +106,38 @@ def test_fast2048_parity_at_measured_geometry(S, T, calls, monkeypatch):
     assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
 
 
+@pytest.mark.parametrize("S,T,calls,opts", [
+    (4096, 16, 1, {}), (2500, 5, 2, {}), (2369, 3, 1, {}), (8192, 8, 1, {}), (4000, 9, 2, {"slope": 0.5, "fast_peaks": True, "rolloff_q": 1.0, "rolloff_rate": 6.0}),
+    (3000, 12, 1, {"gravity": 0.2, "floor": -40}),
+])
+def test_fast2048_split_runs_are_bit_identical_to_whole_streams(S, T, calls, opts, monkeypatch):
+    """Split mode of the warp-per-stream kernel (an SM's frames cut into 16 equal runs: a stream changes warps mid-call through
+    global memory, as it would between two calls) against whole streams per warp (WF_SPLIT=0): every output row, silent flag and
+    the state after the call must be identical — streams with silent stretches (gate: decay -> freeze -> wake) included."""
+    import torch
+    from waveform_b200 import Engine
+
+    monkeypatch.setenv("WF_TEAM_W", "1")
+    settings = {"fft_size": 2048, "window": "hann", "gravity": 0.65, **opts}
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("WF_SPLIT", mode)
+        eng = Engine(settings, channels=1, max_streams=S)
+        pcm = device_pcm(S, 1, (T - 1) * 2048 + 2048, seed=77 + S, zero_every=3, frame_len=2048 * max(1, T // 3))
+        parts, t0 = [], 0
+        for c in range(calls):
+            n = T // calls + (1 if c < T % calls else 0)
+            parts.append(eng.process(pcm[:, :, t0 * 2048:].contiguous(), n, 2048, want_peak=bool(opts)))
+            t0 += n
+        torch.cuda.synchronize()
+        assert eng.last_kernel_name().startswith("stft2048_fast"), eng.last_kernel_name()
+        res[mode] = ({k: torch.cat([q[k] for q in parts], dim=1) for k in ("db", "silent")}, eng.get_state())
+    assert torch.equal(res["1"][0]["db"], res["0"][0]["db"])
+    assert torch.equal(res["1"][0]["silent"], res["0"][0]["silent"])
+    for key in ("tsmooth", "hold_db", "flags"):
+        assert np.array_equal(res["1"][1][key], res["0"][1][key]), key
+
+
 TEAM_SHAPES = [
     # (S, T, calls, W expected): few streams x many ticks (SURVEY §8(d) C3 '256 x 256' family) -> a team of W warps per stream
     (256, 64, 2, 8), (512, 48, 2, 4), (148, 48, 3, 16), (1024, 21, 2, 4), (300, 9, 1, 4), (37, 5, 1, 4), (600, 8, 2, 4), (1184, 6, 1, 4),

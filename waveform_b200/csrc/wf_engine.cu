@@ -45,6 +45,7 @@ struct wf_engine {
     bool use_par16384 = true;   // WF_PAR16384=0: N=16384 stays on the CTA-per-tick kernel (A/B tests)
     bool use_warp2 = true;      // WF_WARP2=0: non-power-of-two sizes stay on the first-generation any-N kernel (A/B tests)
     bool lazy_hold = true;      // WF_LAZY_HOLD=0: always write the mirror (A/B tests)
+    bool split_runs = true;     // WF_SPLIT=0: whole streams per warp in the N=2048 warp-per-stream kernel (A/B tests)
     bool force_generic = false; // WF_FORCE_GENERIC=1: bypass the specialised N=2048 kernel (A/B tests)
     int fast_maxw = 16;         // WF_FAST_MAXW=12|16: which compiled variant of the N=2048 kernel (tuning knob)
     int fast_wpc_override = 0;  // WF_FAST_WPC=n: force warps per CTA (tuning knob)
@@ -589,6 +590,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         e->use_warp2 = !(w2 && w2[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
         e->lazy_hold = !(lh && lh[0] == '0');
+        const char *sp = getenv("WF_SPLIT");
+        e->split_runs = !(sp && sp[0] == '0');
         const char *wo = getenv("WF_FAST_WPC");
         if(wo)
             e->fast_wpc_override = atoi(wo);
@@ -869,6 +872,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         kp.lazy_hold = e->lazy_hold ? 1 : 0;
+        kp.split = e->split_runs ? 1 : 0;
         if(kp.lazy_hold)
             e->hold_implicit = true;
         // Fewer streams than 148 SMs x 16 warps: a team of W warps per stream works on W ticks at once (wf_team2048.cuh).

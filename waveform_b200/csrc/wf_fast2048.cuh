@@ -125,9 +125,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         if(i < 512)
             s_twP[i] = __ldg(p.tw_post + i);
     }
+    volatile int *seg_done = reinterpret_cast<volatile int *>(mbar + 1); // this warp's head segment is finished (split mode)
     if(lane == 0)
     {
         mbar_init(mbar, 1);
+        *seg_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -150,15 +152,86 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
     const int kb = jp + (lane == 0 ? 32 : 0);
     const int k2_q0 = (lane == 0) ? 512 : (kb + 992);
 
-    if(warp < n_local && lane == 0)
+    // ---- work list of this warp ----
+    // Whole streams, dealt round-robin (local index li = warp, warp + W, ...), leave the last round partly empty: 4096 streams
+    // are 27.7 per SM, i.e. 16 busy warps for one round and 11.7 for the second.  In split mode (p.split, at least one
+    // stream per warp, more than one tick) the SM's n_local * T frames are cut into W equal runs of consecutive frames
+    // instead: a warp's run is [tail of stream a][whole streams][head of stream b], and a stream is continued by the next
+    // warp exactly as it would be by the next call (state, flags and mirror go through global memory).  Order inside a
+    // warp: the head first (it depends on nothing), the whole streams, the tail last — by then warp - 1 has long finished
+    // the head it started with; the hand-over is a shared-memory flag behind a CTA-scope fence.
+    const bool split = (p.split != 0) && (n_local >= warps_per_cta) && (T > 1);
+    int u0 = 0, u1 = 0;
+    if(split)
     {
+        const int U = n_local * T, per = (U + warps_per_cta - 1) / warps_per_cta;
+        u0 = min(warp * per, U);
+        u1 = min(u0 + per, U);
+    }
+    const int full0 = (u0 + T - 1) / T, full1 = u1 / T; // whole streams [full0, full1)
+    const int has_head = (split && (u1 % T) != 0) ? 1 : 0, has_tail = (split && (u0 % T) != 0) ? 1 : 0;
+    const int nseg = split ? (has_head + max(full1 - full0, 0) + has_tail)
+                           : ((n_local > warp) ? (n_local - warp + warps_per_cta - 1) / warps_per_cta : 0);
+    // segment j -> (local stream index, first tick, end tick)
+    auto segment = [&](int j, int &li, int &t0, int &t1) {
+        if(!split)
+        {
+            li = warp + j * warps_per_cta;
+            t0 = 0;
+            t1 = T;
+            return;
+        }
+        if(has_head && j == 0)
+        {
+            li = full1;
+            t0 = 0;
+            t1 = u1 % T;
+            return;
+        }
+        j -= has_head;
+        if(j < full1 - full0)
+        {
+            li = full0 + j;
+            t0 = 0;
+            t1 = T;
+            return;
+        }
+        li = u0 / T;
+        t0 = u0 % T;
+        t1 = T;
+    };
+
+    if(nseg > 0 && lane == 0)
+    {
+        int li, t0, t1;
+        segment(0, li, t0, t1);
         mbar_expect_tx(mbar, kN * 4);
-        tma_load_1d(buf, p.pcm + (size_t)(blockIdx.x + warp * G) * p.stream_stride, kN * 4, mbar);
+        tma_load_1d(buf, p.pcm + (size_t)(blockIdx.x + li * G) * p.stream_stride + (size_t)t0 * p.hop, kN * 4, mbar);
     }
 
-    for(int li = warp; li < n_local; li += warps_per_cta)
+    for(int j = 0; j < nseg; ++j)
     {
+        int li, t0, t1;
+        segment(j, li, t0, t1);
         const int s = (int)blockIdx.x + li * G;
+        // the next segment (its first frame and state are prefetched under the last tick of this one)
+        int s_next = -1, t0_next = 0;
+        if(j + 1 < nseg)
+        {
+            int li2, t12;
+            segment(j + 1, li2, t0_next, t12);
+            s_next = (int)blockIdx.x + li2 * G;
+        }
+        if(t0 > 0)
+        {
+            // continuation of a stream whose first ticks the previous warp ran as its head segment
+            const volatile int *prev_done = reinterpret_cast<const volatile int *>(wbase - kWarpBytes + kWarpBufBytes + kStateBytes + 8);
+            if(lane == 0)
+                while(*prev_done == 0)
+                    ;
+            __syncwarp();
+            __threadfence_block();
+        }
         // ---- per-stream state: global (natural bin order) -> shared ([pair][lane]) ----
         {
             const float *sp = p.state + (size_t)s * B;
@@ -177,7 +250,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         float *hold_s = p.hold_db + (size_t)s * B;
 
 #pragma unroll 1
-        for(int t = 0; t < T; ++t)
+        for(int t = t0; t < t1; ++t)
         {
             // ---- frame from shared (TMA-staged), window in the load prologue ----
             mbar_wait(mbar, phase);
@@ -223,16 +296,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
                     // the next stream's EMA state (4 KB, one 128-byte line per lane) is pulled into L2 now, so that the
                     // synchronous state load at the top of the stream loop does not pay DRAM latency (matters when a
                     // stream has few frames: the 65536 x 1 layout loads a state per frame)
-                    if(t + 1 == T && li + warps_per_cta < n_local)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (size_t)(s + warps_per_cta * G) * B + lane * 32));
+                    if(t + 1 == t1 && s_next >= 0 && t0_next == 0)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (size_t)s_next * B + lane * 32));
                     // prefetch the next frame (or the next stream's first frame) under pass B + epilogue
                     if(lane == 0)
                     {
                         const float *next = nullptr;
-                        if(t + 1 < T)
+                        if(t + 1 < t1)
                             next = pcm_s + (size_t)(t + 1) * p.hop;
-                        else if(li + warps_per_cta < n_local)
-                            next = p.pcm + (size_t)(s + warps_per_cta * G) * p.stream_stride;
+                        else if(s_next >= 0)
+                            next = p.pcm + (size_t)s_next * p.stream_stride + (size_t)t0_next * p.hop;
                         if(next != nullptr)
                         {
                             fence_proxy_async();
@@ -417,7 +490,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         // ---- state back to the engine; m_decibels mirror for the next call's gate / hold paths ----
         {
             float *sp = p.state + (size_t)s * B;
-            const float *last = p.out_db + ((size_t)s * T + (T - 1)) * B;
+            const float *last = p.out_db + ((size_t)s * T + (t1 - 1)) * B;
             const bool plain = !EXTRA || (!p.normalize && p.rolloff == nullptr);
             // The mirror equals dbfs(state) after a normal tick without volume / roll-off post-processing: do not spend
             // 4 KB of HBM writes per stream on it, set bit 3 instead (the engine materialises it on demand, see
@@ -449,6 +522,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             }
             if(lane == 0)
                 p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent ? 2u : 0u) | 4u | (lazy ? 8u : 0u));
+        }
+        if(t1 < T)
+        {
+            // head segment: hand the stream to the next warp (state, flags, mirror and output rows are written)
+            __threadfence_block();
+            __syncwarp();
+            if(lane == 0)
+                *seg_done = 1;
         }
         __syncwarp();
     }
