@@ -43,6 +43,7 @@ struct wf_engine {
     std::string last_kernel;    // name of the spectrum kernel the most recent launch_range dispatched to (wf_last_kernel_name)
     bool hold_implicit = false; // some stream may carry flags bit 3 (m_decibels mirror left implicit by the N=2048 kernel)
     bool use_par16384 = true;   // WF_PAR16384=0: N=16384 stays on the CTA-per-tick kernel (A/B tests)
+    bool use_warp2_display = true; // WF_WARP2_DISPLAY=0: display outputs stay on the CTA-per-tick / any-N kernels (A/B tests)
     bool use_warp2 = true;      // WF_WARP2=0: non-power-of-two sizes stay on the first-generation any-N kernel (A/B tests)
     bool lazy_hold = true;      // WF_LAZY_HOLD=0: always write the mirror (A/B tests)
     bool split_runs = true;     // WF_SPLIT=0: whole streams per warp in the N=2048 warp-per-stream kernel (A/B tests)
@@ -588,6 +589,8 @@ int wf_create(const wf_config *cfg, wf_engine **out)
         e->use_par16384 = !(p16 && p16[0] == '0');
         const char *w2 = getenv("WF_WARP2");
         e->use_warp2 = !(w2 && w2[0] == '0');
+        const char *w2d = getenv("WF_WARP2_DISPLAY");
+        e->use_warp2_display = !(w2d && w2d[0] == '0');
         const char *lh = getenv("WF_LAZY_HOLD");
         e->lazy_hold = !(lh && lh[0] == '0');
         const char *sp = getenv("WF_SPLIT");
@@ -919,19 +922,29 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         e->last_kernel = "stft16384_parity_kernel<" + std::to_string((int)x) + "> " + std::to_string(kp.n_streams) + " clusters of 2";
         return WF_OK;
     }
-    // Non-power-of-two sizes with a compiled two-pass plan (wf_warp2.cuh): same launch shape as the N=2048 kernel.
-    const bool warp2_ok = e->use_warp2 && warp2_supported(N) && (cc == 1) && !t.cfg.stereo && kp.out_db && !kp.out_points &&
-                          !kp.out_pixels && !kp.out_min && aligned16;
+    // Non-power-of-two sizes with a compiled two-pass plan (wf_warp2.cuh): same launch shape as the N=2048 kernel.  With
+    // display outputs (curve points / bars / pixels / minimum) the same kernel runs the render-time stages per warp; that
+    // variant also takes the power-of-two sizes 512 / 1024 / 2048 (config 1: N=1024, 26 bars).
+    const bool disp = kp.out_points || kp.out_pixels || kp.out_min;
+    const bool warp2_ok = e->use_warp2 && (cc == 1) && !t.cfg.stereo && aligned16 &&
+                          (disp ? (e->use_warp2_display && !e->force_generic && (warp2_supported(N) || warp2_pow2_supported(N)))
+                                : (warp2_supported(N) && kp.out_db));
     if(warp2_ok)
     {
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         int wpc = 16, grid = 1;
         fast2048_geometry(kp.n_streams, e->sm_count, 16, &wpc, &grid);
+        if(disp) // per warp: the tick's dB row, the display scratch (4 * scratch_q floats), the arg-min scratch
+            kp.disp_bytes = (int)((((size_t)B + 4 * (size_t)kp.scratch_q + 64) * sizeof(float) + 127) / 128 * 128);
         const char *name = "";
-        WF_CUDA(e, warp2_launch(N, x, kp, grid, wpc, st, e->use_pdl, e->device, &name));
-        e->launches++;
-        e->last_kernel = std::string(name) + " N=" + std::to_string(N) + " grid " + std::to_string(grid) + " x " + std::to_string(wpc) + " warps";
-        return WF_OK;
+        const cudaError_t rc = warp2_launch(N, x, disp, kp, grid, &wpc, st, e->use_pdl, e->device, &name);
+        if(rc != cudaErrorInvalidConfiguration) // (a curve too long for one warp's share of shared memory falls through)
+        {
+            WF_CUDA(e, rc);
+            e->launches++;
+            e->last_kernel = std::string(name) + " N=" + std::to_string(N) + " grid " + std::to_string(grid) + " x " + std::to_string(wpc) + " warps";
+            return WF_OK;
+        }
     }
     return (cc == 2) ? dispatch_n<2>(e, kp, st, extra) : dispatch_n<1>(e, kp, st, extra);
 }

@@ -59,6 +59,7 @@ struct KParams {
     float vol_target, max_gain;
     int write_hold;   // write final m_decibels mirror to hold_db at the end of the call
     int lazy_hold;    // N=2048 warp-per-stream kernel: leave the mirror implicit (flags bit 3) when it equals dbfs(state)
+    int disp_bytes;   // warp-per-stream kernels with display outputs: extra shared memory per warp (dB row + display scratch)
     int split;        // N=2048 warp-per-stream kernel: cut an SM's frames into equal runs per warp (streams may change warps mid-call)
     // interpolation
     const float *interp_idx;

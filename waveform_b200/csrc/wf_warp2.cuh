@@ -54,7 +54,11 @@ struct Geo {
 
 } // namespace warp2
 
-template<int L, int P, bool EXTRA>
+// DISP: the render-time stages (interpolation to curve points / bars, Gaussian, pixels, running minimum; display_stage<32> of
+// wf_kernels.cuh, the one the CTA-per-tick kernels use) run on the warp right after the tick's dB row, which is then kept
+// in a per-warp shared-memory row (it doubles as the "previous row" of the hold paths; out_db may be null).  The extra
+// per-warp area (p.disp_bytes: dB row, display scratch, arg-min scratch) follows the regular per-warp areas.
+template<int L, int P, bool EXTRA, bool DISP = false>
 __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_kernel(const __grid_constant__ KParams p)
 {
     using namespace fast;
@@ -71,6 +75,13 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
     float2 *buf = reinterpret_cast<float2 *>(wbase);
     float2 *sst = reinterpret_cast<float2 *>(wbase + G::kBufBytes) + lane;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase + G::kBufBytes + G::kStateBytes);
+    float *dbs = nullptr, *disp_pts = nullptr, *disp_red = nullptr;
+    if constexpr(DISP)
+    {
+        dbs = reinterpret_cast<float *>(smem_raw + G::kTableBytes + (size_t)warps_per_cta * G::kWarpBytes + (size_t)warp * p.disp_bytes);
+        disp_pts = dbs + B;
+        disp_red = disp_pts + 4 * p.scratch_q;
+    }
 
     for(int i = threadIdx.x; i < M; i += blockDim.x)
     {
@@ -216,7 +227,8 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
                     }
                 }
             }
-            float *odb = p.out_db + ((size_t)s * T + t) * B;
+            const bool wr_db = !DISP || (p.out_db != nullptr);
+            float *odb = wr_db ? p.out_db + ((size_t)s * T + t) * B : nullptr;
             float vc = 0.0f;
             if(EXTRA && p.normalize)
             {
@@ -290,12 +302,19 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
                     if(k1 >= 1)
                         peak = fmaxf(peak, d1);
                     outs &= !(d1 > p.floor_m10);
-                    if(act_b)
+                    if(act_b && wr_db)
                         stg_stream(odb + k1, d1);
                     peak = (k2 >= 0) ? fmaxf(peak, d2) : peak;
                     outs &= (k2 < 0) | !(d2 > p.floor_m10);
-                    if(st2)
+                    if(st2 && wr_db)
                         stg_stream(odb + k2c, d2);
+                    if constexpr(DISP)
+                    {
+                        if(act_b)
+                            dbs[k1] = d1;
+                        if(st2)
+                            dbs[k2c] = d2;
+                    }
                 });
                 outs |= !act_b;
                 peak = act_b ? peak : -INFINITY;
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
             else
             {
                 // tick returned early (hold) or the channel was skipped while the tick went on (stale dB re-converted)
-                const float *prev_db = (t > 0) ? (odb - B) : hold_s;
+                const float *prev_db = (t > 0) ? (DISP ? dbs : (odb - B)) : hold_s; // DISP: the row kept in shared memory
 #pragma unroll 1
                 for(int k = lane; k < B; k += 32)
                 {
@@ -322,8 +341,17 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
                     outs &= !(o > p.floor_m10);
                     if(k >= 1)
                         peak = fmaxf(peak, o);
-                    odb[k] = o;
+                    if(wr_db)
+                        odb[k] = o;
+                    if constexpr(DISP)
+                        dbs[k] = o;
                 }
+            }
+            if constexpr(DISP)
+            {
+                __syncwarp();
+                display_stage<32>(p, dbs, disp_pts, B, 1, (size_t)s * T + t, lane, true, disp_red);
+                __syncwarp();
             }
             if(gate && !last_silent)
                 prev_out_silent = __all_sync(0xffffffffu, outs);
@@ -354,7 +382,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
         }
         if(p.write_hold && T > 0)
         {
-            const float *last = p.out_db + ((size_t)s * T + (T - 1)) * B;
+            const float *last = DISP ? dbs : p.out_db + ((size_t)s * T + (T - 1)) * B;
             __syncwarp();
             for(int k = lane; k < B; k += 32)
                 hold_s[k] = last[k];

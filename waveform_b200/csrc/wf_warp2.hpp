@@ -6,7 +6,10 @@ namespace wf {
 struct KParams;
 // true when a compiled (L, P) plan exists for this fft size
 bool warp2_supported(int N);
-// warps = warps per CTA (1..16), grid = CTAs; extra = slope / fast peaks / skip mask / volume / roll-off / peak output in use
-cudaError_t warp2_launch(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+// power-of-two sizes with a plan (routed here only for display outputs)
+bool warp2_pow2_supported(int N);
+// *warps = warps per CTA (1..16; lowered if the display scratch does not fit), grid = CTAs; extra = slope / fast peaks / skip
+// mask / volume / roll-off / peak output in use; disp = display outputs (points / pixels / minimum) requested
+cudaError_t warp2_launch(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                          const char **name);
 } // namespace wf

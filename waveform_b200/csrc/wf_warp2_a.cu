@@ -3,7 +3,7 @@
 
 namespace wf {
 
-cudaError_t warp2_launch_b(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch_b(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                            const char **name);
 
 bool warp2_supported(int N)
@@ -19,7 +19,7 @@ bool warp2_supported(int N)
     }
 }
 
-cudaError_t warp2_launch(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                          const char **name)
 {
     using namespace warp2;
@@ -31,7 +31,7 @@ cudaError_t warp2_launch(int N, bool extra, const KParams &kp, int grid, int war
         WF_WARP2_CASE(960, 20, 24)   // 48 kHz / 50 fps
         WF_WARP2_CASE(1456, 26, 28)  // 44.1 kHz / 30 fps (1470 & -16): 2^4 7 13
         WF_WARP2_CASE(1600, 25, 32)  // 48 kHz / 30 fps
-    default: return warp2_launch_b(N, extra, kp, grid, warps, st, pdl, device, name);
+    default: return warp2_launch_b(N, extra, disp, kp, grid, warps, st, pdl, device, name);
     }
 }
 

@@ -3,12 +3,14 @@
 
 namespace wf {
 
-cudaError_t warp2_launch_c(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch_c(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                            const char **name);
-cudaError_t warp2_launch_d(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch_e(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
+                           const char **name);
+cudaError_t warp2_launch_d(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                            const char **name);
 
-cudaError_t warp2_launch_b(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch_b(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                            const char **name)
 {
     using namespace warp2;
@@ -22,8 +24,10 @@ cudaError_t warp2_launch_b(int N, bool extra, const KParams &kp, int grid, int w
         WF_WARP2_CASE(1920, 30, 32)
     default: break;
     }
-    const cudaError_t rc = warp2_launch_c(N, extra, kp, grid, warps, st, pdl, device, name);
-    return (rc == cudaErrorInvalidValue) ? warp2_launch_d(N, extra, kp, grid, warps, st, pdl, device, name) : rc;
+    cudaError_t rc = warp2_launch_c(N, extra, disp, kp, grid, warps, st, pdl, device, name);
+    if(rc == cudaErrorInvalidValue)
+        rc = warp2_launch_d(N, extra, disp, kp, grid, warps, st, pdl, device, name);
+    return (rc == cudaErrorInvalidValue) ? warp2_launch_e(N, extra, disp, kp, grid, warps, st, pdl, device, name) : rc;
 }
 
 } // namespace wf

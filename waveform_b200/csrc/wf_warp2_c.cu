@@ -3,7 +3,7 @@
 
 namespace wf {
 
-cudaError_t warp2_launch_c(int N, bool extra, const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device,
+cudaError_t warp2_launch_c(int N, bool extra, bool disp, const KParams &kp, int grid, int *warps, cudaStream_t st, bool pdl, int device,
                            const char **name)
 {
     using namespace warp2;

@@ -6,38 +6,51 @@
 namespace wf {
 namespace warp2 {
 
-template<int L, int P, bool EXTRA>
-cudaError_t launch(const KParams &kp, int grid, int warps, cudaStream_t st, bool pdl, int device)
+constexpr int kMaxSmem = 227 * 1024; // opt-in shared memory per CTA on sm_100
+
+template<int L, int P, bool EXTRA, bool DISP>
+cudaError_t launch(const KParams &kp, int grid, int *warps_io, cudaStream_t st, bool pdl, int device)
 {
     using G = Geo<L, P>;
     static thread_local bool configured[64] = {false};
     const int dev = device & 63;
     if(!configured[dev])
     {
-        cudaError_t err = cudaFuncSetAttribute(stft_warp2_kernel<L, P, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               G::smem_bytes(G::kWarps));
+        cudaError_t err = cudaFuncSetAttribute(stft_warp2_kernel<L, P, EXTRA, DISP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               DISP ? kMaxSmem : G::smem_bytes(G::kWarps));
         if(err != cudaSuccess)
             return err;
         configured[dev] = true;
     }
+    int warps = *warps_io;
+    const size_t per_warp_extra = DISP ? (size_t)kp.disp_bytes : 0;
+    while(warps > 1 && G::smem_bytes(warps) + warps * per_warp_extra > (size_t)kMaxSmem)
+        --warps; // display scratch (curves with many points) costs warps per SM; the streams simply take more rounds
+    if(G::smem_bytes(warps) + warps * per_warp_extra > (size_t)kMaxSmem)
+        return cudaErrorInvalidConfiguration;
+    *warps_io = warps;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)(warps * 32));
-    cfg.dynamicSmemBytes = G::smem_bytes(warps);
+    cfg.dynamicSmemBytes = G::smem_bytes(warps) + warps * per_warp_extra;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, stft_warp2_kernel<L, P, EXTRA>, kp);
+    return cudaLaunchKernelEx(&cfg, stft_warp2_kernel<L, P, EXTRA, DISP>, kp);
 }
 
+// (display outputs always take the EXTRA = true instantiation: one more kernel per plan instead of two)
 #define WF_WARP2_CASE(NN, LL, PP_)                                                                                       \
     case NN:                                                                                                             \
         static_assert(2 * LL * PP_ == NN, "plan");                                                                      \
-        *name = "stft_warp2_kernel<" #LL "," #PP_ ">";                                                                   \
-        return extra ? launch<LL, PP_, true>(kp, grid, warps, st, pdl, device) : launch<LL, PP_, false>(kp, grid, warps, st, pdl, device);
+        *name = disp ? "stft_warp2_kernel<" #LL "," #PP_ ",display>" : "stft_warp2_kernel<" #LL "," #PP_ ">";          \
+        if(disp)                                                                                                         \
+            return launch<LL, PP_, true, true>(kp, grid, warps, st, pdl, device);                                        \
+        return extra ? launch<LL, PP_, true, false>(kp, grid, warps, st, pdl, device)                                    \
+                     : launch<LL, PP_, false, false>(kp, grid, warps, st, pdl, device);
 
 } // namespace warp2
 } // namespace wf
