@@ -218,6 +218,50 @@ def test_other_kernels_parity_at_scale(settings, channels, S, T, hop_div, want_p
     _run_and_check(settings, channels, S, T, hop_div=hop_div, want_points=want_points, n_random=24, calls=2)
 
 
+WARP2_DISPLAY_CASES = [
+    # (settings, S, T): BASELINE config 1 (N=1024, 26 Catmull-Rom bars), the automatic size with a filtered Lanczos curve,
+    # N=2048 curve, a radix-7/13 size with bars, nearest-point interpolation
+    ({"fft_size": 1024, "window": "hann", "display_mode": "bars", "interp_mode": "catmull_rom"}, 2048, 6),
+    ({"fft_size": 800, "window": "hann", "interp_mode": "lanczos", "filter_mode": "gauss"}, 1500, 5),
+    ({"fft_size": 2048, "window": "hann", "interp_mode": "catmull_rom", "slope": 0.5, "rolloff_q": 1.0, "rolloff_rate": 6.0}, 300, 7),
+    ({"fft_size": 1456, "window": "blackman", "display_mode": "bars", "interp_mode": "lanczos", "floor": -40, "gravity": 0.2}, 700, 9),
+    ({"fft_size": 512, "window": "hann", "interp_mode": "point"}, 37, 4),
+]
+
+
+@pytest.mark.parametrize("settings,S,T", WARP2_DISPLAY_CASES)
+def test_warp2_display_variant(settings, S, T, monkeypatch):
+    """Display outputs of one-channel sources on the warp-per-stream kernel (stft_warp2_kernel<L,P,display>: the render-time
+    stages run per warp on a dB row kept in shared memory): parity of spectrum, points and silent flags with the oracle at
+    real stream counts with silent stretches; identical points / pixels / minimum with and without the dB output (the hold
+    paths then read the shared-memory row instead of the previous output row); and against the CTA-per-tick / any-N path."""
+    import torch
+    from waveform_b200 import Engine
+
+    eng, out, pcm = _run_and_check(settings, 1, S, T, want_points=True, n_random=24, calls=2)
+    assert "display" in eng.last_kernel_name(), eng.last_kernel_name()
+    N = eng.fft_size
+    a = Engine(settings, channels=1, max_streams=S).process(pcm, T, N, want_points=True, want_pixels=True)
+    e2 = Engine(settings, channels=1, max_streams=S)
+    b = e2.process(pcm, T, N, want_db=False, want_points=True, want_pixels=True)
+    torch.cuda.synchronize()
+    assert "display" in e2.last_kernel_name()
+    for key in ("points", "pixels", "min", "silent"):
+        assert torch.equal(a[key], b[key]), key
+    monkeypatch.setenv("WF_WARP2_DISPLAY", "0")
+    e3 = Engine(settings, channels=1, max_streams=S)
+    c = e3.process(pcm, T, N, want_points=True, want_pixels=True)
+    torch.cuda.synchronize()
+    assert "display" not in e3.last_kernel_name()
+    assert torch.equal(a["silent"], c["silent"])
+    d = (a["points"] - c["points"]).abs()
+    assert float(d.median()) < 1e-4 and float(d.max()) < 5e-2, (float(d.median()), float(d.max()))
+    dp = (a["pixels"] - c["pixels"]).abs()
+    assert float(dp.max()) < 5e-2 * max(1.0, float(c["pixels"].abs().max()) / 100.0), float(dp.max())
+    same_min = (a["min"][..., 1] == c["min"][..., 1]).float().mean()
+    assert float(same_min) > 0.98, float(same_min)   # the arg-min position can move between two near-equal pixels
+
+
 GOLD = sorted((Path(__file__).parent / "golden").glob("case_*.npz"))
 
 

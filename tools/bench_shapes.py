@@ -20,6 +20,11 @@ SHAPES = [
     ("N=800 (auto size 48k/60fps) 4096x16", {"fft_size": 800, "window": "hann"}, 1, 4096, 16, 800, "db"),
     ("N=1920 4096x16", {"fft_size": 1920, "window": "hann"}, 1, 4096, 16, 1920, "db"),
     ("N=1600 4096x16", {"fft_size": 1600, "window": "hann"}, 1, 4096, 16, 1600, "db"),
+    # display outputs of one-channel sources (render-time stages fused; WF_WARP2_DISPLAY=0 puts them back on the CTA-per-tick /
+    # any-N kernels)
+    ("disp N=800 Catmull-Rom curve, points out", {"fft_size": 800, "window": "hann", "interp_mode": "catmull_rom"}, 1, 4096, 16, 800, "points"),
+    ("disp N=2048 Lanczos curve, points out", {"fft_size": 2048, "window": "hann", "interp_mode": "lanczos"}, 1, 4096, 16, 2048, "points"),
+    ("disp N=2048 Lanczos curve, bins + points", {"fft_size": 2048, "window": "hann", "interp_mode": "lanczos"}, 1, 4096, 16, 2048, "db+points"),
 ]
 
 

@@ -934,8 +934,19 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         int wpc = 16, grid = 1;
         fast2048_geometry(kp.n_streams, e->sm_count, 16, &wpc, &grid);
-        if(disp) // per warp: the tick's dB row, the display scratch (4 * scratch_q floats), the arg-min scratch
-            kp.disp_bytes = (int)((((size_t)B + 4 * (size_t)kp.scratch_q + 64) * sizeof(float) + 127) / 128 * 128);
+        if(disp)
+        {
+            // shared memory of the display variant (layout in wf_warp2.cuh): per CTA the setup tables, per warp the tick's dB
+            // row, the bar sample points and — only for the Gaussian / pixel / minimum outputs — two rows of points + scratch
+            const size_t n_idx = (kp.n_sample > 0) ? (size_t)kp.n_sample : (size_t)kp.n_points;
+            const size_t n_w = (kp.interp_mode != 0) ? n_idx * (size_t)kp.taps : 0;
+            const size_t tab = ((n_w + 3) & ~(size_t)3) + n_idx + (kp.filter ? (size_t)kp.gauss_size : 0) +
+                               (kp.display_bar ? 2 * (size_t)kp.n_points : 0);
+            const bool need_pts = kp.filter || kp.out_pixels || kp.out_min;
+            const size_t per_warp = (size_t)B + (size_t)kp.n_sample + (need_pts ? 2 * (size_t)kp.n_points + 64 : 0);
+            kp.disp_tab_bytes = (int)((tab * sizeof(float) + 127) / 128 * 128);
+            kp.disp_bytes = (int)((per_warp * sizeof(float) + 127) / 128 * 128);
+        }
         const char *name = "";
         const cudaError_t rc = warp2_launch(N, x, disp, kp, grid, &wpc, st, e->use_pdl, e->device, &name);
         if(rc != cudaErrorInvalidConfiguration) // (a curve too long for one warp's share of shared memory falls through)

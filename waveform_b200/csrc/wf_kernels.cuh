@@ -60,6 +60,7 @@ struct KParams {
     int write_hold;   // write final m_decibels mirror to hold_db at the end of the call
     int lazy_hold;    // N=2048 warp-per-stream kernel: leave the mirror implicit (flags bit 3) when it equals dbfs(state)
     int disp_bytes;   // warp-per-stream kernels with display outputs: extra shared memory per warp (dB row + display scratch)
+    int disp_tab_bytes; // ... and per CTA (the display stage's setup tables)
     int split;        // N=2048 warp-per-stream kernel: cut an SM's frames into equal runs per warp (streams may change warps mid-call)
     // interpolation
     const float *interp_idx;
@@ -374,17 +375,36 @@ struct Fft<N, PlanT<TN_, R0, Rest...>> {
     }
 };
 
+// The display stage's setup tables (interpolation indices / weights, bar bands, Gaussian): in global memory, read through
+// the non-coherent path (LDG = true: the CTA-per-tick kernels), or copied once per CTA into shared memory by a persistent
+// kernel (LDG = false: the warp-per-stream kernels, which evaluate ~n_points kernel sums per warp and tick).
+struct DispTab {
+    const float *interp_idx;
+    const float *interp_w;
+    const int *band_widths;
+    const int *band_offsets;
+    const float *gauss_w;
+};
+template<bool LDG, class T>
+__device__ __forceinline__ T tab_ld(const T *q)
+{
+    if constexpr(LDG)
+        return __ldg(q);
+    else
+        return *q;
+}
+
 // kernel_convolve, src/filter.hpp:160-169 (sequential mul+add, no contraction).  Away from the spectrum's edges the
 // window is complete: all taps' weights (one or two 128-bit loads) and samples are fetched first, then accumulated in
 // the reference's order — same rounding, no load latency inside the dependent chain.
-template<int TAPS>
+template<int TAPS, bool LDG>
 __device__ __forceinline__ float kernel_convolve_full(const float *db, const float *__restrict__ w)
 {
     float wt[TAPS], x[TAPS];
 #pragma unroll
     for(int q = 0; q < TAPS / 4; ++q)
     {
-        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(w) + q);
+        const float4 w4 = tab_ld<LDG>(reinterpret_cast<const float4 *>(w) + q);
         wt[4 * q] = w4.x;
         wt[4 * q + 1] = w4.y;
         wt[4 * q + 2] = w4.z;
@@ -399,6 +419,7 @@ __device__ __forceinline__ float kernel_convolve_full(const float *db, const flo
         sum = __fadd_rn(sum, __fmul_rn(x[i], wt[i]));
     return sum;
 }
+template<bool LDG>
 __device__ __forceinline__ float kernel_convolve(const float *db, int sz, const float *__restrict__ w, int radius, int index)
 {
     const int start = (index - radius) + 1;
@@ -406,47 +427,19 @@ __device__ __forceinline__ float kernel_convolve(const float *db, int sz, const 
     if(start >= 0 && index + radius + 1 <= sz)
     {
         if(radius == 4)
-            return kernel_convolve_full<8>(db + start, w); // Lanczos a = 4
+            return kernel_convolve_full<8, LDG>(db + start, w); // Lanczos a = 4
         if(radius == 2)
-            return kernel_convolve_full<4>(db + start, w); // Catmull-Rom
+            return kernel_convolve_full<4, LDG>(db + start, w); // Catmull-Rom
     }
     float sum = 0.0f;
     for(int i = max(start, 0); i < stop; ++i)
-        sum = __fadd_rn(sum, __fmul_rn(db[i], __ldg(w + (i - start))));
+        sum = __fadd_rn(sum, __fmul_rn(db[i], tab_ld<LDG>(w + (i - start))));
     return sum;
 }
 
-// One display point (curve) or one bar from the dB spectrum of a display channel held in shared memory.
-// src/filter.hpp:182-211, src/source.cpp:1392-1394,1523-1532
-__device__ __forceinline__ float interp_point(const KParams &p, const float *db, int B, int i)
-{
-    if(!p.display_bar)
-    {
-        const float x = __ldg(p.interp_idx + i);
-        if(p.interp_mode == 0)
-            return db[(int)x];
-        return kernel_convolve(db, B, p.interp_w + (size_t)i * p.taps, p.radius, (int)x);
-    }
-    const int count = __ldg(p.band_widths + i);
-    float sum = 0.0f;
-    if(p.interp_mode == 0)
-    {
-        const int base = (int)__ldg(p.interp_idx + i);
-        for(int j = 0; j < count; ++j)
-            sum = __fadd_rn(sum, db[base + j]);
-    }
-    else
-    {
-        const int off = __ldg(p.band_offsets + i);
-        for(int j = 0; j < count; ++j)
-            sum = __fadd_rn(sum, kernel_convolve(db, B, p.interp_w + (size_t)(off + j) * p.taps, p.radius,
-                                                 (int)__ldg(p.interp_idx + off + j)));
-    }
-    return __fdiv_rn(sum, (float)count);
-}
-
 // weighted_avg, src/filter.hpp:133-158
-__device__ __forceinline__ float weighted_avg(const KParams &p, const float *samples, int n, int index)
+template<bool LDG>
+__device__ __forceinline__ float weighted_avg(const KParams &p, const DispTab &tb, const float *samples, int n, int index)
 {
     const int start = (index - p.gauss_radius) + 1;
     const int stop = index + p.gauss_radius;
@@ -458,14 +451,14 @@ __device__ __forceinline__ float weighted_avg(const KParams &p, const float *sam
         float wsum = 0.0f;
         for(int i = loopstart; i < loopstop; ++i)
         {
-            const float weight = __ldg(p.gauss_w + (i - start));
+            const float weight = tab_ld<LDG>(tb.gauss_w + (i - start));
             wsum = __fadd_rn(wsum, weight);
             sum = __fadd_rn(sum, __fmul_rn(samples[i], weight));
         }
         return __fdiv_rn(sum, wsum);
     }
     for(int i = start; i < stop; ++i)
-        sum = __fadd_rn(sum, __fmul_rn(samples[i], __ldg(p.gauss_w + (i - start))));
+        sum = __fadd_rn(sum, __fmul_rn(samples[i], tab_ld<LDG>(tb.gauss_w + (i - start))));
     return __fdiv_rn(sum, p.gauss_sum);
 }
 
@@ -486,50 +479,146 @@ __device__ __forceinline__ float std_lerp_dev(float a, float b, float t)
 //   -> dB -> pixel height (lerp/clamp), running (miny, minpos), frequency-axis mirroring
 //      (src/source.cpp:1408-1424 curve, :1548-1565 bars) -> out_pixels / out_min
 // `pts` is scratch for [2][dch][n_points] (+ [dch][n_sample]) floats: 4 * scratch_q floats per stream.  TN threads (one group) cooperate; SYNC() is the group barrier.
+// A kernel sum with all TAPS taps.  Complete window: straight loads.  At the spectrum's edges the reference shortens the loop
+// (src/filter.hpp:160-169); here the missing taps get weight 0 and a clamped address instead: adding x*0 = +-0 to the running
+// sum leaves it unchanged (the skipped terms are leading or trailing, x is a finite dB value, the sum starts at +0), so the
+// result is the same bit for bit without a divergent variable-length loop on the ~20 % of a log-frequency curve that sits
+// on the first few bins.
+template<int TAPS, bool LDG>
+__device__ __forceinline__ float kernel_sum(const float *db, int sz, const float *__restrict__ w, int index)
+{
+    const int start = index - TAPS / 2 + 1;
+    float wt[TAPS], x[TAPS];
+#pragma unroll
+    for(int q = 0; q < TAPS / 4; ++q)
+    {
+        const float4 w4 = tab_ld<LDG>(reinterpret_cast<const float4 *>(w) + q);
+        wt[4 * q] = w4.x;
+        wt[4 * q + 1] = w4.y;
+        wt[4 * q + 2] = w4.z;
+        wt[4 * q + 3] = w4.w;
+    }
+    if(start >= 0 && start + TAPS <= sz)
+    {
+#pragma unroll
+        for(int i = 0; i < TAPS; ++i)
+            x[i] = db[start + i];
+    }
+    else
+    {
+#pragma unroll
+        for(int i = 0; i < TAPS; ++i)
+        {
+            const int j = start + i;
+            const bool ok = (unsigned)j < (unsigned)sz;
+            x[i] = db[ok ? j : 0];
+            wt[i] = ok ? wt[i] : 0.0f;
+        }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for(int i = 0; i < TAPS; ++i)
+        sum = __fadd_rn(sum, __fmul_rn(x[i], wt[i]));
+    return sum;
+}
+
+// value of sample point q of the interpolation tables; TAPS: 0 = nearest bin, 4 / 8 = Catmull-Rom / Lanczos kernel,
+// -1 = any other radius (run-time loop)
+template<bool LDG, int TAPS>
+__device__ __forceinline__ float interp_at(const KParams &p, const DispTab &tb, const float *db, int B, int q)
+{
+    const int index = (int)tab_ld<LDG>(tb.interp_idx + q);
+    if constexpr(TAPS == 0)
+        return db[index];
+    else if constexpr(TAPS > 0)
+        return kernel_sum<TAPS, LDG>(db, B, tb.interp_w + (size_t)q * TAPS, index);
+    else
+        return kernel_convolve<LDG>(db, B, tb.interp_w + (size_t)q * p.taps, p.radius, index);
+}
+
+// Interpolation to display points (curve) or bars, with the mode tests outside the point loops.
+template<int TN, bool LDG, int TAPS>
+__device__ __forceinline__ void display_points(const KParams &p, const DispTab &tb, const float *dbs, float *raw, float *tmp, int B,
+                                               int dch, size_t tick, int tid, bool active, bool need_smem)
+{
+    const int np = p.n_points;
+    auto put = [&](int d, int i, float val) {
+        if(need_smem)
+            raw[d * np + i] = val;
+        else if(active)
+            stg_stream(p.out_points + (tick * dch + d) * np + i, val);
+    };
+    if(!p.display_bar)
+    {
+        for(int d = 0; d < dch; ++d)
+            for(int i = tid; i < np; i += TN)
+                put(d, i, interp_at<LDG, TAPS>(p, tb, dbs + d * B, B, i));
+        return;
+    }
+    if constexpr(TAPS == 0)
+    {
+        // bars without a kernel: the mean of the band's bins (src/filter.hpp:195-211)
+        for(int d = 0; d < dch; ++d)
+            for(int i = tid; i < np; i += TN)
+            {
+                const int count = tab_ld<LDG>(tb.band_widths + i);
+                const float *src = dbs + d * B + (int)tab_ld<LDG>(tb.interp_idx + i);
+                float sum = 0.0f;
+                for(int j = 0; j < count; ++j)
+                    sum = __fadd_rn(sum, src[j]);
+                put(d, i, __fdiv_rn(sum, (float)count));
+            }
+    }
+    else
+    {
+        // Bars with an interpolation kernel: a bar is the mean of band_width kernel sums and the high-frequency bars are wide,
+        // so one thread per bar would leave the group waiting for the widest bar.  Phase A evaluates every sample point of
+        // every band in parallel; phase B adds them per bar in the reference's order.
+        for(int d = 0; d < dch; ++d)
+            for(int q = tid; q < p.n_sample; q += TN)
+                tmp[d * p.n_sample + q] = interp_at<LDG, TAPS>(p, tb, dbs + d * B, B, q);
+        group_sync<TN>();
+        for(int d = 0; d < dch; ++d)
+            for(int i = tid; i < np; i += TN)
+            {
+                const int count = tab_ld<LDG>(tb.band_widths + i);
+                const float *src = tmp + d * p.n_sample + tab_ld<LDG>(tb.band_offsets + i);
+                float sum = 0.0f;
+                for(int j = 0; j < count; ++j)
+                    sum = __fadd_rn(sum, src[j]);
+                put(d, i, __fdiv_rn(sum, (float)count));
+            }
+    }
+}
+
+template<int TN, bool LDG>
+__device__ __forceinline__ void display_stage_tab(const KParams &p, const DispTab &tb, const float *dbs, float *pts, float *tmp,
+                                                  int B, int dch, size_t tick, int tid, bool active, float *red);
 template<int TN>
 __device__ __forceinline__ void display_stage(const KParams &p, const float *dbs, float *pts, int B, int dch, size_t tick,
                                               int tid, bool active, float *red)
+{
+    const DispTab tb{p.interp_idx, p.interp_w, p.band_widths, p.band_offsets, p.gauss_w};
+    display_stage_tab<TN, true>(p, tb, dbs, pts, pts + 4 * p.n_points, B, dch, tick, tid, active, red);
+}
+// `tmp`: [dch][n_sample] floats (bars with an interpolation kernel), `pts`: [2][dch][n_points] floats (only touched when the
+// Gaussian, pixel or minimum outputs are on), `red`: 2 * TN floats (pixel minimum only).
+template<int TN, bool LDG>
+__device__ __forceinline__ void display_stage_tab(const KParams &p, const DispTab &tb, const float *dbs, float *pts, float *tmp,
+                                                  int B, int dch, size_t tick, int tid, bool active, float *red)
 {
     const int np = p.n_points;
     const bool need_smem = p.filter || (p.out_pixels != nullptr) || (p.out_min != nullptr);
     float *raw = pts;                 // interpolated points
     float *fin = pts + dch * np;      // after the Gaussian (or alias of raw)
-    // Bars with an interpolation kernel: a bar is the mean of band_width kernel sums (src/filter.hpp:195-211) and the
-    // high-frequency bars are wide, so one thread per bar would leave the group waiting for the widest bar.  Phase A
-    // evaluates every sample point of every band in parallel; phase B adds them per bar in the reference's order.
-    const bool two_phase = p.display_bar && p.interp_mode != 0 && p.n_sample > 0;
-    float *tmp = pts + 4 * np;        // [dch][n_sample]
-    if(two_phase)
-    {
-        for(int d = 0; d < dch; ++d)
-            for(int q = tid; q < p.n_sample; q += TN)
-                tmp[d * p.n_sample + q] =
-                    kernel_convolve(dbs + d * B, B, p.interp_w + (size_t)q * p.taps, p.radius, (int)__ldg(p.interp_idx + q));
-        group_sync<TN>();
-    }
-    for(int d = 0; d < dch; ++d)
-    {
-        const float *db = dbs + d * B;
-        for(int i = tid; i < np; i += TN)
-        {
-            float val;
-            if(two_phase)
-            {
-                const int count = __ldg(p.band_widths + i);
-                const float *src = tmp + d * p.n_sample + __ldg(p.band_offsets + i);
-                float sum = 0.0f;
-                for(int j = 0; j < count; ++j)
-                    sum = __fadd_rn(sum, src[j]);
-                val = __fdiv_rn(sum, (float)count);
-            }
-            else
-                val = interp_point(p, db, B, i);
-            if(need_smem)
-                raw[d * np + i] = val;
-            else if(active)
-                stg_stream(p.out_points + (tick * dch + d) * np + i, val);
-        }
-    }
+    if(p.interp_mode == 0 || (p.display_bar && p.n_sample <= 0))
+        display_points<TN, LDG, 0>(p, tb, dbs, raw, tmp, B, dch, tick, tid, active, need_smem);
+    else if(p.radius == 4 && p.taps == 8)
+        display_points<TN, LDG, 8>(p, tb, dbs, raw, tmp, B, dch, tick, tid, active, need_smem);
+    else if(p.radius == 2 && p.taps == 4)
+        display_points<TN, LDG, 4>(p, tb, dbs, raw, tmp, B, dch, tick, tid, active, need_smem);
+    else
+        display_points<TN, LDG, -1>(p, tb, dbs, raw, tmp, B, dch, tick, tid, active, need_smem);
     if(!need_smem)
         return;
     group_sync<TN>();
@@ -537,7 +626,7 @@ __device__ __forceinline__ void display_stage(const KParams &p, const float *dbs
     {
         for(int d = 0; d < dch; ++d)
             for(int i = tid; i < np; i += TN)
-                fin[d * np + i] = weighted_avg(p, raw + d * np, np, i);
+                fin[d * np + i] = weighted_avg<LDG>(p, tb, raw + d * np, np, i);
         group_sync<TN>();
     }
     else

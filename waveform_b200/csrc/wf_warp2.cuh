@@ -75,12 +75,39 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
     float2 *buf = reinterpret_cast<float2 *>(wbase);
     float2 *sst = reinterpret_cast<float2 *>(wbase + G::kBufBytes) + lane;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(wbase + G::kBufBytes + G::kStateBytes);
-    float *dbs = nullptr, *disp_pts = nullptr, *disp_red = nullptr;
+    // DISP: [CTA: interpolation weights | indices | Gaussian | band widths | band offsets] (p.disp_tab_bytes, copied once
+    // below: a persistent CTA reads them n_points times per warp and tick) then per warp [dB row | bar samples | points x 2 |
+    // arg-min scratch] (p.disp_bytes; the last two only for the Gaussian / pixel / minimum outputs) — wf_engine.cu sizes both
+    float *dbs = nullptr, *disp_tmp = nullptr, *disp_pts = nullptr, *disp_red = nullptr;
+    DispTab dtab{};
     if constexpr(DISP)
     {
-        dbs = reinterpret_cast<float *>(smem_raw + G::kTableBytes + (size_t)warps_per_cta * G::kWarpBytes + (size_t)warp * p.disp_bytes);
-        disp_pts = dbs + B;
-        disp_red = disp_pts + 4 * p.scratch_q;
+        unsigned char *db0 = smem_raw + G::kTableBytes + (size_t)warps_per_cta * G::kWarpBytes;
+        const int n_idx = (p.n_sample > 0) ? p.n_sample : p.n_points;
+        const int n_w = (p.interp_mode != 0) ? n_idx * p.taps : 0;
+        const int n_g = p.filter ? p.gauss_size : 0, n_b = p.display_bar ? p.n_points : 0;
+        float *t_w = reinterpret_cast<float *>(db0);
+        float *t_idx = t_w + ((n_w + 3) & ~3);
+        float *t_g = t_idx + n_idx;
+        int *t_bw = reinterpret_cast<int *>(t_g + n_g);
+        int *t_bo = t_bw + n_b;
+        for(int i = threadIdx.x; i < n_w; i += blockDim.x)
+            t_w[i] = __ldg(p.interp_w + i);
+        for(int i = threadIdx.x; i < n_idx; i += blockDim.x)
+            t_idx[i] = __ldg(p.interp_idx + i);
+        for(int i = threadIdx.x; i < n_g; i += blockDim.x)
+            t_g[i] = __ldg(p.gauss_w + i);
+        for(int i = threadIdx.x; i < n_b; i += blockDim.x)
+        {
+            t_bw[i] = __ldg(p.band_widths + i);
+            t_bo[i] = (p.band_offsets != nullptr) ? __ldg(p.band_offsets + i) : 0;
+        }
+        dtab = DispTab{t_idx, t_w, t_bw, t_bo, t_g};
+        const bool need_pts = p.filter || (p.out_pixels != nullptr) || (p.out_min != nullptr);
+        dbs = reinterpret_cast<float *>(db0 + p.disp_tab_bytes + (size_t)warp * p.disp_bytes);
+        disp_tmp = dbs + B;
+        disp_pts = disp_tmp + p.n_sample;
+        disp_red = disp_pts + (need_pts ? 2 * p.n_points : 0);
     }
 
     for(int i = threadIdx.x; i < M; i += blockDim.x)
@@ -350,7 +377,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
             if constexpr(DISP)
             {
                 __syncwarp();
-                display_stage<32>(p, dbs, disp_pts, B, 1, (size_t)s * T + t, lane, true, disp_red);
+                display_stage_tab<32, false>(p, dtab, dbs, disp_pts, disp_tmp, B, 1, (size_t)s * T + t, lane, true, disp_red);
                 __syncwarp();
             }
             if(gate && !last_silent)

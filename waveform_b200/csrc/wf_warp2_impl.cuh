@@ -23,16 +23,16 @@ cudaError_t launch(const KParams &kp, int grid, int *warps_io, cudaStream_t st, 
         configured[dev] = true;
     }
     int warps = *warps_io;
-    const size_t per_warp_extra = DISP ? (size_t)kp.disp_bytes : 0;
-    while(warps > 1 && G::smem_bytes(warps) + warps * per_warp_extra > (size_t)kMaxSmem)
-        --warps; // display scratch (curves with many points) costs warps per SM; the streams simply take more rounds
-    if(G::smem_bytes(warps) + warps * per_warp_extra > (size_t)kMaxSmem)
+    const size_t per_warp_extra = DISP ? (size_t)kp.disp_bytes : 0, cta_extra = DISP ? (size_t)kp.disp_tab_bytes : 0;
+    while(warps > 1 && G::smem_bytes(warps) + cta_extra + warps * per_warp_extra > (size_t)kMaxSmem)
+        --warps; // the display rows cost warps per SM at the largest sizes; the streams simply take more rounds
+    if(G::smem_bytes(warps) + cta_extra + warps * per_warp_extra > (size_t)kMaxSmem)
         return cudaErrorInvalidConfiguration;
     *warps_io = warps;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)(warps * 32));
-    cfg.dynamicSmemBytes = G::smem_bytes(warps) + warps * per_warp_extra;
+    cfg.dynamicSmemBytes = G::smem_bytes(warps) + cta_extra + warps * per_warp_extra;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
