@@ -42,13 +42,13 @@ cudaError_t launch(const KParams &kp, int grid, int *warps_io, cudaStream_t st, 
     return cudaLaunchKernelEx(&cfg, stft_warp2_kernel<L, P, EXTRA, DISP>, kp);
 }
 
-// (display outputs always take the EXTRA = true instantiation: one more kernel per plan instead of two)
 #define WF_WARP2_CASE(NN, LL, PP_)                                                                                       \
     case NN:                                                                                                             \
         static_assert(2 * LL * PP_ == NN, "plan");                                                                      \
         *name = disp ? "stft_warp2_kernel<" #LL "," #PP_ ",display>" : "stft_warp2_kernel<" #LL "," #PP_ ">";          \
         if(disp)                                                                                                         \
-            return launch<LL, PP_, true, true>(kp, grid, warps, st, pdl, device);                                        \
+            return extra ? launch<LL, PP_, true, true>(kp, grid, warps, st, pdl, device)                                 \
+                         : launch<LL, PP_, false, true>(kp, grid, warps, st, pdl, device);                               \
         return extra ? launch<LL, PP_, true, false>(kp, grid, warps, st, pdl, device)                                    \
                      : launch<LL, PP_, false, false>(kp, grid, warps, st, pdl, device);
 
