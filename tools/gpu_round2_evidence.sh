@@ -14,7 +14,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft2048_team -s 3 -c 1 -o gpurun_out/r02_team2048 \
     python bench.py --streams 256 --frames 256 --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-layouts --no-c5 --e2e-steps 1 > gpurun_out/r02_ncu_team.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft_warp2 -s 3 -c 1 -o gpurun_out/r02_warp2_800 \
-    python tools/bench_shapes.py "--only=N=800" --iters=1 > gpurun_out/r02_ncu_warp2.log 2>&1
+    python tools/bench_shapes.py "--only=N=800 (auto" --iters=1 > gpurun_out/r02_ncu_warp2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:stft_warp2 -s 3 -c 1 -o gpurun_out/r02_warp2_display_800 \
+    python tools/bench_shapes.py "--only=disp N=800" --iters=1 > gpurun_out/r02_ncu_warp2d.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:wave_chunk -s 3 -c 1 -o gpurun_out/r02_wave_chunk \
     python tools/bench_meter.py > gpurun_out/r02_ncu_wave.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:meter_fused -s 3 -c 1 -o gpurun_out/r02_meter_fused \
@@ -23,5 +25,5 @@ timeout 400 python tools/bench_shapes.py 2>&1 | tee gpurun_out/r02_shapes.txt
 timeout 300 python tools/bench_next_rows.py 2>&1 | tee gpurun_out/r02_next_rows.txt
 timeout 200 python tools/bench_meter.py 2>&1 | tee gpurun_out/r02_meter.txt
 PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 400 compute-sanitizer --tool memcheck python tools/sanitize.py 2>&1 | tail -6 | tee gpurun_out/r02_sanitizer.txt
-PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 300 compute-sanitizer --tool racecheck python tools/sanitize.py --next-rows 2>&1 | tail -3 | tee -a gpurun_out/r02_sanitizer.txt
+PYTORCH_NO_CUDA_MEMORY_CACHING=1 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize.py 2>&1 | tail -3 | tee -a gpurun_out/r02_sanitizer.txt
 ls -la gpurun_out/*.ncu-rep

@@ -19,7 +19,11 @@ CASES = [({"fft_size": 2048}, 1, 20, 3, 1, False),
          ({"fft_size": 2048, "gravity": 0.3, "floor": -40}, 1, 3, 37, 1, False),
          ({"fft_size": 800}, 1, 40, 5, 1, False),
          ({"fft_size": 1920, "slope": 0.5, "fast_peaks": True}, 1, 9, 4, 2, False),
-         ({"fft_size": 1456}, 1, 5, 3, 1, False)]
+         ({"fft_size": 1456}, 1, 5, 3, 1, False),
+         # display variant of the warp-per-stream kernel (tables + dB row in shared memory), split runs of the headline kernel
+         ({"fft_size": 1024, "display_mode": "bars", "interp_mode": "catmull_rom"}, 1, 5, 4, 1, True),
+         ({"fft_size": 2048, "interp_mode": "lanczos", "filter_mode": "gauss"}, 1, 3, 3, 2, True),
+         ({"fft_size": 2048}, 1, 2400, 3, 1, False)]
 ONLY_NEXT = "--next-rows" in sys.argv   # meter / feed / waveform only (short enough for racecheck)
 for s, ch, S, T, hopdiv, pts in ([] if ONLY_NEXT else CASES):
     e = Engine(s, channels=ch, max_streams=S); N = e.fft_size; hop = N // hopdiv

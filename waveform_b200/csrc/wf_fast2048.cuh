@@ -160,7 +160,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
     // warp exactly as it would be by the next call (state, flags and mirror go through global memory).  Order inside a
     // warp: the head first (it depends on nothing), the whole streams, the tail last — by then warp - 1 has long finished
     // the head it started with; the hand-over is a shared-memory flag behind a CTA-scope fence.
-    const bool split = (p.split != 0) && (n_local >= warps_per_cta) && (T > 1);
+    // (worth it only when the partly empty last round costs more than the hand-overs: the makespan shrinks by
+    // (rounds * W - n_local) * T / W frame times, each of the W - 1 hand-overs adds a state round trip)
+    const int rounds_whole = (n_local + warps_per_cta - 1) / warps_per_cta;
+    const bool split = (p.split != 0) && (n_local >= warps_per_cta) && (T > 1) &&
+                       (2 * (rounds_whole * warps_per_cta - n_local) * T > 3 * warps_per_cta);
     int u0 = 0, u1 = 0;
     if(split)
     {
