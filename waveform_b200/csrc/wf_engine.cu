@@ -938,10 +938,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         {
             // shared memory of the display variant (layout in wf_warp2.cuh): per CTA the setup tables, per warp the tick's dB
             // row, the bar sample points and — only for the Gaussian / pixel / minimum outputs — two rows of points + scratch
-            const size_t n_idx = (kp.n_sample > 0) ? (size_t)kp.n_sample : (size_t)kp.n_points;
-            const size_t n_w = (kp.interp_mode != 0) ? n_idx * (size_t)kp.taps : 0;
-            const size_t tab = ((n_w + 3) & ~(size_t)3) + n_idx + (kp.filter ? (size_t)kp.gauss_size : 0) +
-                               (kp.display_bar ? 2 * (size_t)kp.n_points : 0);
+            const size_t tab = display_table_floats(kp);
             const bool need_pts = kp.filter || kp.out_pixels || kp.out_min;
             const size_t per_warp = (size_t)B + (size_t)kp.n_sample + (need_pts ? 2 * (size_t)kp.n_points + 64 : 0);
             kp.disp_tab_bytes = (int)((tab * sizeof(float) + 127) / 128 * 128);

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         if(i < 512)
             s_twP[i] = __ldg(p.tw_post + i);
     }
-    volatile int *seg_done = reinterpret_cast<volatile int *>(mbar + 1); // this warp's head segment is finished (split mode)
+    int *seg_done = reinterpret_cast<int *>(mbar + 1); // this warp's head segment is finished (split mode)
     if(lane == 0)
     {
         mbar_init(mbar, 1);
@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
         if(t0 > 0)
         {
             // continuation of a stream whose first ticks the previous warp ran as its head segment
-            const volatile int *prev_done = reinterpret_cast<const volatile int *>(wbase - kWarpBytes + kWarpBufBytes + kStateBytes + 8);
+            // (atomics on the flag, fences around them: the hand-over is a release / acquire pair at CTA scope)
+            int *prev_done = reinterpret_cast<int *>(wbase - kWarpBytes + kWarpBufBytes + kStateBytes + 8);
             if(lane == 0)
-                while(*prev_done == 0)
+                while(atomicAdd(prev_done, 0) == 0)
                     ;
             __syncwarp();
             __threadfence_block();
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) stft2048_fast_kernel(const __gri
             __threadfence_block();
             __syncwarp();
             if(lane == 0)
-                *seg_done = 1;
+                atomicExch(seg_done, 1);
         }
         __syncwarp();
     }

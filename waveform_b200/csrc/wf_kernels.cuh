@@ -385,6 +385,37 @@ struct DispTab {
     const int *band_offsets;
     const float *gauss_w;
 };
+// floats of shared memory the tables take (weights padded to 16 bytes first, then indices, Gaussian, band widths, band offsets)
+__host__ __device__ inline size_t display_table_floats(const KParams &p)
+{
+    const size_t n_idx = (p.n_sample > 0) ? (size_t)p.n_sample : (size_t)p.n_points;
+    const size_t n_w = (p.interp_mode != 0) ? n_idx * (size_t)p.taps : 0;
+    return ((n_w + 3) & ~(size_t)3) + n_idx + (p.filter ? (size_t)p.gauss_size : 0) + (p.display_bar ? 2 * (size_t)p.n_points : 0);
+}
+// copies the tables to `base` (16-byte aligned shared memory) with `nthreads` threads; the caller synchronises afterwards
+__device__ __forceinline__ DispTab stage_display_tables(const KParams &p, float *base, int tid, int nthreads)
+{
+    const int n_idx = (p.n_sample > 0) ? p.n_sample : p.n_points;
+    const int n_w = (p.interp_mode != 0) ? n_idx * p.taps : 0;
+    const int n_g = p.filter ? p.gauss_size : 0, n_b = p.display_bar ? p.n_points : 0;
+    float *t_w = base;
+    float *t_idx = t_w + ((n_w + 3) & ~3);
+    float *t_g = t_idx + n_idx;
+    int *t_bw = reinterpret_cast<int *>(t_g + n_g);
+    int *t_bo = t_bw + n_b;
+    for(int i = tid; i < n_w; i += nthreads)
+        t_w[i] = __ldg(p.interp_w + i);
+    for(int i = tid; i < n_idx; i += nthreads)
+        t_idx[i] = __ldg(p.interp_idx + i);
+    for(int i = tid; i < n_g; i += nthreads)
+        t_g[i] = __ldg(p.gauss_w + i);
+    for(int i = tid; i < n_b; i += nthreads)
+    {
+        t_bw[i] = __ldg(p.band_widths + i);
+        t_bo[i] = (p.band_offsets != nullptr) ? __ldg(p.band_offsets + i) : 0;
+    }
+    return DispTab{t_idx, t_w, t_bw, t_bo, t_g};
+}
 template<bool LDG, class T>
 __device__ __forceinline__ T tab_ld(const T *q)
 {

@@ -98,6 +98,9 @@ __device__ __forceinline__ void par16384_body(const KParams &p, const v3::Tw3 &t
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // distributed shared memory (the lazy gate reduction) may only be addressed once both CTAs of the cluster are running
+    cluster_arrive();
+    cluster_wait();
     if(use_tma && T > 0 && tid == 0)
     {
         fast::mbar_expect_tx(mbar, (uint32_t)kStageBytes);

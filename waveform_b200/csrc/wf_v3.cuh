@@ -308,6 +308,12 @@ __global__ void __launch_bounds__(v3::Geo3<N>::TN, v3::Geo3<N>::MINB)
     const bool stereo = p.stereo != 0;
     const bool want_points = (p.out_points != nullptr) || (p.out_pixels != nullptr) || (p.out_min != nullptr);
     const bool mirror_each_frame = (p.out_db == nullptr) && p.write_hold;
+    if constexpr(R > 1)
+    {
+        // distributed shared memory may only be addressed once every CTA of the cluster has started executing
+        cluster_arrive();
+        cluster_wait();
+    }
     const uint32_t inbox_sa0 = smem_u32(inbox0);
     const uint32_t dbfull_sa = smem_u32(dbfull);
 

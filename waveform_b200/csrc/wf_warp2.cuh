@@ -83,26 +83,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
     if constexpr(DISP)
     {
         unsigned char *db0 = smem_raw + G::kTableBytes + (size_t)warps_per_cta * G::kWarpBytes;
-        const int n_idx = (p.n_sample > 0) ? p.n_sample : p.n_points;
-        const int n_w = (p.interp_mode != 0) ? n_idx * p.taps : 0;
-        const int n_g = p.filter ? p.gauss_size : 0, n_b = p.display_bar ? p.n_points : 0;
-        float *t_w = reinterpret_cast<float *>(db0);
-        float *t_idx = t_w + ((n_w + 3) & ~3);
-        float *t_g = t_idx + n_idx;
-        int *t_bw = reinterpret_cast<int *>(t_g + n_g);
-        int *t_bo = t_bw + n_b;
-        for(int i = threadIdx.x; i < n_w; i += blockDim.x)
-            t_w[i] = __ldg(p.interp_w + i);
-        for(int i = threadIdx.x; i < n_idx; i += blockDim.x)
-            t_idx[i] = __ldg(p.interp_idx + i);
-        for(int i = threadIdx.x; i < n_g; i += blockDim.x)
-            t_g[i] = __ldg(p.gauss_w + i);
-        for(int i = threadIdx.x; i < n_b; i += blockDim.x)
-        {
-            t_bw[i] = __ldg(p.band_widths + i);
-            t_bo[i] = (p.band_offsets != nullptr) ? __ldg(p.band_offsets + i) : 0;
-        }
-        dtab = DispTab{t_idx, t_w, t_bw, t_bo, t_g};
+        dtab = stage_display_tables(p, reinterpret_cast<float *>(db0), threadIdx.x, blockDim.x);
         const bool need_pts = p.filter || (p.out_pixels != nullptr) || (p.out_min != nullptr);
         dbs = reinterpret_cast<float *>(db0 + p.disp_tab_bytes + (size_t)warp * p.disp_bytes);
         disp_tmp = dbs + B;

@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(Geo<N>::TN, Geo<N>::MINB) stft_wide_kernel(con
     if((int)r < T)
         F::load_raw(v, pcm_s + (size_t)r * p.hop, p, tid); // channel 0 of my first tick
 
+    // distributed shared memory may only be addressed once every CTA of the cluster has started executing
+    cluster_arrive();
+    cluster_wait();
     for(int t0 = 0; t0 < T; t0 += R)
     {
         const int nf = min(R, T - t0);
