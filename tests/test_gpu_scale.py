@@ -138,6 +138,33 @@ def test_fast2048_split_runs_are_bit_identical_to_whole_streams(S, T, calls, opt
         assert np.array_equal(res["1"][1][key], res["0"][1][key]), key
 
 
+@pytest.mark.parametrize("N,S,T,points", [(800, 4096, 16, False), (1920, 2500, 5, False), (1456, 3000, 7, False), (800, 4000, 6, True),
+                                          (1024, 2500, 5, True)])
+def test_warp2_split_runs_are_bit_identical_to_whole_streams(N, S, T, points, monkeypatch):
+    """The same equal-runs split in stft_warp2_kernel (non-power-of-two sizes and the display variant, where the first tick of a
+    continued stream takes its previous row from the mirror instead of the warp's shared-memory row)."""
+    import torch
+    from waveform_b200 import Engine
+
+    settings = {"fft_size": N, "window": "hann", "gravity": 0.3, "floor": -40}
+    if points:
+        settings["interp_mode"] = "catmull_rom"
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("WF_SPLIT", mode)
+        eng = Engine(settings, channels=1, max_streams=S)
+        pcm = device_pcm(S, 1, T * N, seed=5 + N, zero_every=3, frame_len=N * max(1, T // 3))
+        a = eng.process(pcm[:, :, : 2 * N].contiguous(), 2, N, want_points=points, want_pixels=points)
+        b = eng.process(pcm[:, :, 2 * N:].contiguous(), T - 2, N, want_points=points, want_pixels=points)
+        torch.cuda.synchronize()
+        assert eng.last_kernel_name().startswith("stft_warp2"), eng.last_kernel_name()
+        res[mode] = ({k: torch.cat([a[k], b[k]], dim=1) for k in a}, eng.get_state())
+    for k in res["1"][0]:
+        assert torch.equal(res["1"][0][k], res["0"][0][k]), k
+    for key in ("tsmooth", "hold_db", "flags"):
+        assert np.array_equal(res["1"][1][key], res["0"][1][key]), key
+
+
 TEAM_SHAPES = [
     # (S, T, calls, W expected): few streams x many ticks (SURVEY §8(d) C3 '256 x 256' family) -> a team of W warps per stream
     (256, 64, 2, 8), (512, 48, 2, 4), (148, 48, 3, 16), (1024, 21, 2, 4), (300, 9, 1, 4), (37, 5, 1, 4), (600, 8, 2, 4), (1184, 6, 1, 4),

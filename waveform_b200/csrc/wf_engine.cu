@@ -934,6 +934,7 @@ static int launch_range(wf_engine *e, const wf_batch *b, cudaStream_t st, int s0
         const bool x = kp.slope || kp.rolloff || kp.normalize || kp.fast_peaks || kp.skip_mask || kp.out_peak || kp.g_tab;
         int wpc = 16, grid = 1;
         fast2048_geometry(kp.n_streams, e->sm_count, 16, &wpc, &grid);
+        kp.split = e->split_runs ? 1 : 0;
         if(disp)
         {
             // shared memory of the display variant (layout in wf_warp2.cuh): per CTA the setup tables, per warp the tick's dB

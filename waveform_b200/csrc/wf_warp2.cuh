@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
         const int k = (i & 31) + P * (i >> 5);
         s_twP[i] = ((i & 31) < P && k < M) ? __ldg(p.tw_post + k) : make_float2(1.0f, 0.0f);
     }
+    int *seg_done = reinterpret_cast<int *>(mbar + 1); // split mode: this warp's head segment is finished
     if(lane == 0)
     {
         mbar_init(mbar, 1);
+        *seg_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -125,15 +127,81 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
     // second bin of pair q: lane != 0: (P - lane) + P (L-1-q); lane 0: P (L - q) (q >= 1); q == 0 on lane 0: M/2 if L is even
     const int kb2 = (lb == 0) ? 0 : (P - lb);
 
-    if(warp < n_local && lane == 0)
+    // ---- work list of this warp: whole streams dealt round-robin, or (split mode, see wf_fast2048.cuh) the SM's n_local * T
+    // frames cut into equal runs [tail of stream a][whole streams][head of stream b]; a stream changes warps through global
+    // memory (state, flags, mirror) behind a shared-memory flag, exactly as it would between two calls ----
+    const int rounds_whole = (n_local + warps_per_cta - 1) / warps_per_cta;
+    const bool split = (p.split != 0) && (n_local >= warps_per_cta) && (T > 1) &&
+                       (2 * (rounds_whole * warps_per_cta - n_local) * T > 3 * warps_per_cta);
+    int u0 = 0, u1 = 0;
+    if(split)
     {
+        const int U = n_local * T, per = (U + warps_per_cta - 1) / warps_per_cta;
+        u0 = min(warp * per, U);
+        u1 = min(u0 + per, U);
+    }
+    const int full0 = (u0 + T - 1) / T, full1 = u1 / T;
+    const int has_head = (split && (u1 % T) != 0) ? 1 : 0, has_tail = (split && (u0 % T) != 0) ? 1 : 0;
+    const int nseg = split ? (has_head + max(full1 - full0, 0) + has_tail)
+                           : ((n_local > warp) ? (n_local - warp + warps_per_cta - 1) / warps_per_cta : 0);
+    auto segment = [&](int j, int &li, int &t0, int &t1) {
+        if(!split)
+        {
+            li = warp + j * warps_per_cta;
+            t0 = 0;
+            t1 = T;
+            return;
+        }
+        if(has_head && j == 0)
+        {
+            li = full1;
+            t0 = 0;
+            t1 = u1 % T;
+            return;
+        }
+        j -= has_head;
+        if(j < full1 - full0)
+        {
+            li = full0 + j;
+            t0 = 0;
+            t1 = T;
+            return;
+        }
+        li = u0 / T;
+        t0 = u0 % T;
+        t1 = T;
+    };
+
+    if(nseg > 0 && lane == 0)
+    {
+        int li, t0, t1;
+        segment(0, li, t0, t1);
         mbar_expect_tx(mbar, N * 4);
-        tma_load_1d(buf, p.pcm + (size_t)(blockIdx.x + warp * GR) * p.stream_stride, N * 4, mbar);
+        tma_load_1d(buf, p.pcm + (size_t)(blockIdx.x + li * GR) * p.stream_stride + (size_t)t0 * p.hop, N * 4, mbar);
     }
 
-    for(int li = warp; li < n_local; li += warps_per_cta)
+    for(int j = 0; j < nseg; ++j)
     {
+        int li, t0, t1;
+        segment(j, li, t0, t1);
         const int s = (int)blockIdx.x + li * GR;
+        int s_next = -1, t0_next = 0;
+        if(j + 1 < nseg)
+        {
+            int li2, t12;
+            segment(j + 1, li2, t0_next, t12);
+            s_next = (int)blockIdx.x + li2 * GR;
+        }
+        if(t0 > 0)
+        {
+            // continuation of a stream whose first ticks the previous warp ran as its head segment
+            int *prev_done = reinterpret_cast<int *>(wbase - G::kWarpBytes + G::kBufBytes + G::kStateBytes + 8);
+            if(lane == 0)
+                while(atomicAdd(prev_done, 0) == 0)
+                    ;
+            __syncwarp();
+            __threadfence_block();
+        }
         float *state_s = p.state + (size_t)s * B;
         // second-bin index of this lane for pair q (negative = no such bin)
         auto k2_of = [&](int q) -> int {
@@ -161,7 +229,7 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
         float *hold_s = p.hold_db + (size_t)s * B;
 
 #pragma unroll 1
-        for(int t = 0; t < T; ++t)
+        for(int t = t0; t < t1; ++t)
         {
             mbar_wait(mbar, phase);
             phase ^= 1u;
@@ -198,15 +266,15 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
             for(int n1 = 0; n1 < L; ++n1)
                 v[n1] = buf64[n1 * PP + lb];
             __syncwarp(); // all generic-proxy accesses to buf are done: it can take the next frame
-            if(t + 1 == T && li + warps_per_cta < n_local)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (size_t)(s + warps_per_cta * GR) * B + (lane * 32) % B));
+            if(t + 1 == t1 && s_next >= 0 && t0_next == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.state + (size_t)s_next * B + (lane * 32) % B));
             if(lane == 0)
             {
                 const float *next = nullptr;
-                if(t + 1 < T)
+                if(t + 1 < t1)
                     next = pcm_s + (size_t)(t + 1) * p.hop;
-                else if(li + warps_per_cta < n_local)
-                    next = p.pcm + (size_t)(s + warps_per_cta * GR) * p.stream_stride;
+                else if(s_next >= 0)
+                    next = p.pcm + (size_t)s_next * p.stream_stride + (size_t)t0_next * p.hop;
                 if(next != nullptr)
                 {
                     fence_proxy_async();
@@ -330,7 +398,9 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
             else
             {
                 // tick returned early (hold) or the channel was skipped while the tick went on (stale dB re-converted)
-                const float *prev_db = (t > 0) ? (DISP ? dbs : (odb - B)) : hold_s; // DISP: the row kept in shared memory
+                // the previous tick's row: the output row, or (DISP) the row kept in shared memory; at the first tick of a
+                // segment the mirror, which the previous call — or the warp that ran the stream's first ticks — left behind
+                const float *prev_db = (t > t0) ? (DISP ? dbs : (odb - B)) : hold_s;
 #pragma unroll 1
                 for(int k = lane; k < B; k += 32)
                 {
@@ -390,13 +460,21 @@ __global__ void __launch_bounds__(warp2::Geo<L, P>::kWarps * 32, 1) stft_warp2_k
         }
         if(p.write_hold && T > 0)
         {
-            const float *last = DISP ? dbs : p.out_db + ((size_t)s * T + (T - 1)) * B;
+            const float *last = DISP ? dbs : p.out_db + ((size_t)s * T + (t1 - 1)) * B;
             __syncwarp();
             for(int k = lane; k < B; k += 32)
                 hold_s[k] = last[k];
         }
         if(lane == 0)
             p.flags[s] = (unsigned char)((last_silent ? 1u : 0u) | (prev_out_silent ? 2u : 0u) | 4u);
+        if(t1 < T)
+        {
+            // head segment: hand the stream to the next warp (state, flags, mirror and output rows are written)
+            __threadfence_block();
+            __syncwarp();
+            if(lane == 0)
+                atomicExch(seg_done, 1);
+        }
         __syncwarp();
     }
 }
