@@ -28,12 +28,48 @@ CASES = [
 
 @pytest.mark.parametrize("settings,channels", CASES)
 def test_oracle_matches_compiled_reference(settings, channels):
+    _compare(settings, channels)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_randomised_settings_oracle_vs_compiled_reference(seed):
+    """Differential fuzz of the oracle against the unmodified reference over the settings space the GPU fuzz
+    (tests/test_gpu_scale.py::test_randomised_configs_against_oracle) draws from, plus the display options: every table bit for bit,
+    every tick's spectrum within the parity criterion, silent flags and points."""
+    rng = np.random.default_rng(4000 + seed)
+    N = int(rng.choice([128, 512, 1024, 2048, 4096, 8192, 800, 720, 1600, 1920, 1456, 352, 2000, 4160, 1088]))
+    mode = str(rng.choice(["mono", "mono", "stereo"]))
+    channels = 2 if mode == "stereo" or rng.uniform() < 0.25 else 1
+    settings = {"fft_size": N, "channel_mode": mode,
+                "window": str(rng.choice(["none", "hann", "hamming", "blackman", "blackman_harris", "power_of_sine"])),
+                "temporal_smoothing": str(rng.choice(["none", "exp_moving_avg", "exp_moving_avg", "tv_exp_moving_avg"])),
+                "gravity": float(rng.choice([0.2, 0.5, 0.65, 0.9])), "floor": int(rng.choice([-30, -45, -65])),
+                "display_mode": str(rng.choice(["curve", "curve", "bars"])),
+                "interp_mode": str(rng.choice(["point", "lanczos", "catmull_rom"])),
+                "log_scale": bool(rng.uniform() < 0.8)}
+    if settings["window"] == "power_of_sine":
+        settings["sine_exponent"] = int(rng.choice([1, 2, 3, 4]))
+    if rng.uniform() < 0.3:
+        settings.update(slope=float(rng.choice([0.25, 1.0])), fast_peaks=bool(rng.uniform() < 0.5))
+    if rng.uniform() < 0.3:
+        settings.update(rolloff_q=1.0, rolloff_rate=float(rng.choice([3.0, 9.0])))
+    if rng.uniform() < 0.3:
+        settings.update(filter_mode="gauss", filter_radius=float(rng.choice([1.5, 2.5])))
+    if rng.uniform() < 0.2:
+        settings["normalize_volume"] = True
+    if settings["display_mode"] == "bars" and rng.uniform() < 0.5:
+        settings.update(bar_width=int(rng.choice([2, 4, 24])), bar_gap=int(rng.choice([0, 1, 6])))
+    hop_div = int(rng.choice([1, 2, 4]))
+    _compare(settings, channels, T=int(rng.choice([6, 14, 30])), hop_div=hop_div, seed=seed)
+
+
+def _compare(settings, channels, T=30, hop_div=2, seed=11):
     ref = refbind.RefSource(settings, impl=refbind.IMPL_GENERIC, channels=channels)
     orc = OracleSource(settings, channels=channels)
-    N, T = ref.fft_size, 30
-    hop = N // 2
+    N = ref.fft_size
+    hop = N // hop_div
     cc = ref.capture_channels
-    x = synth_pcm(1, cc, (T - 1) * hop + N, seed=11)[0]
+    x = synth_pcm(1, cc, (T - 1) * hop + N, seed=seed)[0]
     x[:, 6 * hop: 6 * hop + 4 * N] = 0
     if cc == 2:
         x[1, 12 * hop:] = 0  # one channel goes silent: exercises the stale-dB quirk
