@@ -54,6 +54,33 @@ def test_meter_oracle_is_bit_exact_vs_compiled_reference(settings, ch, hop):
     assert ref["silent"].sum() > 0 or settings.get("floor", -65) < -60
 
 
+@pytest.mark.parametrize("seed", range(30))
+def test_meter_oracle_randomised_settings_bit_exact_vs_compiled_reference(seed):
+    """Differential fuzz of the level-meter oracle against the unmodified reference (generic path): random window, mode,
+    smoothing, gravity, floor, packet size and channel count, with a silent stretch."""
+    refbind = pytest.importorskip("oracle.refbind")
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle.oraclebind import OracleMeter
+
+    rng = np.random.default_rng(9000 + seed)
+    ch = int(rng.choice([1, 2]))
+    settings = {"meter_buf": int(rng.choice([5, 10, 20, 50, 100, 150, 300])), "rms_mode": bool(rng.uniform() < 0.5),
+                "temporal_smoothing": str(rng.choice(["none", "exp_moving_avg", "tv_exp_moving_avg"])),
+                "gravity": float(rng.choice([0.2, 0.4, 0.65, 0.9])), "floor": int(rng.choice([-30, -40, -65])),
+                "fast_peaks": bool(rng.uniform() < 0.4)}
+    hop = int(rng.choice([97, 441, 480, 800, 801, 1024, 1601]))
+    T = 50
+    pcm = _case_pcm(ch, T, hop)[0] * np.float32(rng.choice([1.0, 0.1, 0.01]))
+    r = refbind.RefSource({"display_mode": "level_meter", **settings}, channels=ch)
+    ref = r.run_meter(pcm, T, hop)
+    o = OracleMeter(settings, channels=ch)
+    assert o.window == r.fft_size
+    out = o.run(pcm, T, hop)
+    for key in ("db", "lin", "silent"):
+        assert np.array_equal(ref[key], out[key]), (key, settings, hop)
+
+
 @pytest.mark.parametrize("ch", [1, 2])
 def test_rms_feed_oracle_is_bit_exact_vs_compiled_reference(ch):
     refbind = pytest.importorskip("oracle.refbind")

@@ -53,6 +53,38 @@ def test_wave_oracle_is_bit_exact_vs_compiled_reference(settings, ch, hop):
     assert np.array_equal(ref["silent"], out["silent"])
 
 
+@pytest.mark.parametrize("seed", range(30))
+def test_wave_oracle_randomised_settings_bit_exact_vs_compiled_reference(seed):
+    """Differential fuzz of the waveform-mode oracle against the unmodified reference: random width, window length, packet size,
+    channel layout, volume normalisation, stretches of zeros and of full-scale samples (the all-zero silent rule's raw material)."""
+    refbind = pytest.importorskip("oracle.refbind")
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    from oracle.oraclebind import OracleWave
+
+    rng = np.random.default_rng(7000 + seed)
+    ch = int(rng.choice([1, 2]))
+    settings = {"width": int(rng.choice([64, 200, 301, 640, 800, 1000, 1920])), "meter_buf": int(rng.choice([5, 10, 20, 50, 150, 500]))}
+    if rng.uniform() < 0.5:
+        settings["channel_mode"] = "stereo"
+    if rng.uniform() < 0.3:
+        settings["normalize_volume"] = True
+    hop = int(rng.choice([97, 333, 441, 480, 800, 1024, 1600, 2000]))
+    T = 60
+    pcm = synth_pcm(1, ch, T * hop, seed=seed)
+    a, b = sorted(int(v) for v in rng.integers(0, T, size=2))
+    pcm[:, :, a * hop: (a + (b - a) // 2) * hop] = 1.0
+    pcm[:, :, (a + (b - a) // 2) * hop: b * hop] = 0.0
+    if ch == 2 and rng.uniform() < 0.4:
+        pcm[:, 1] = 0.0
+    rms = (0.05 + 0.2 * rng.uniform(size=(1, T))).astype(np.float32) if settings.get("normalize_volume") else None
+    r = refbind.RefSource({"display_mode": "waveform", **settings}, channels=ch)
+    ref = r.run_wave(pcm[0], T, hop, rms=None if rms is None else rms[0])
+    out = OracleWave(settings, channels=ch).run(pcm[0], T, hop, rms=None if rms is None else rms[0])
+    assert np.array_equal(ref["out"], out["out"]), settings
+    assert np.array_equal(ref["silent"], out["silent"]), settings
+
+
 @pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])
 def test_wave_oracle_against_reference_golden_vectors(path):
     from oracle.oraclebind import OracleWave
