@@ -160,6 +160,46 @@ def test_gpu_wave_parity_vs_oracle(settings, ch, hop, device_ptrs):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_gpu_wave_randomised_settings_vs_oracle(seed):
+    """Differential fuzz of the chunked waveform kernel against the oracle (itself bit-exact against the reference over the
+    same settings space, test_wave_oracle_randomised_settings_bit_exact_vs_compiled_reference): point pattern and silent flags
+    exactly, dB values to 1e-4 dB; three streams: plain signal, full-scale / zero stretches, a silent second channel."""
+    from waveform_b200 import WaveEngine
+
+    rng = np.random.default_rng(7000 + seed)
+    ch = int(rng.choice([1, 2]))
+    settings = {"width": int(rng.choice([64, 200, 301, 640, 800, 1000, 1920])), "meter_buf": int(rng.choice([5, 10, 20, 50, 150, 500]))}
+    if rng.uniform() < 0.5:
+        settings["channel_mode"] = "stereo"
+    if rng.uniform() < 0.3:
+        settings["normalize_volume"] = True
+    hop = int(rng.choice([97, 333, 441, 480, 800, 1024, 1600, 2000]))
+    S, T = 3, 40
+    pcm = synth_pcm(S, ch, T * hop, seed=seed)
+    a, b = sorted(int(v) for v in rng.integers(0, T, size=2))
+    pcm[1, :, a * hop: (a + (b - a) // 2) * hop] = 1.0
+    pcm[1, :, (a + (b - a) // 2) * hop: b * hop] = 0.0
+    pcm[2, -1] = 0.0
+    rms = (0.05 + 0.2 * rng.uniform(size=(S, T))).astype(np.float32) if settings.get("normalize_volume") else None
+    ref, ref_sil = _oracle_batch(settings, ch, pcm, T, hop, rms)
+    cut = int(rng.integers(1, T))
+    eng = WaveEngine(settings, channels=ch, max_streams=S)
+    p1 = eng.process(pcm[:, :, : cut * hop], cut, hop, input_rms=None if rms is None else rms[:, :cut])
+    p2 = eng.process(pcm[:, :, cut * hop:], T - cut, hop, input_rms=None if rms is None else rms[:, cut:])
+    out = np.concatenate([p1["out"], p2["out"]], axis=1)
+    sil = np.concatenate([p1["silent"], p2["silent"]], axis=1)
+    assert np.array_equal(sil, ref_sil), (settings, ch, hop)
+    lo = ref < -700.0
+    assert np.array_equal(out < -700.0, lo), (settings, ch, hop)
+    untouched = ref == np.float32(-758.59564)
+    assert np.array_equal(out[untouched], ref[untouched])
+    raw = (~lo) & (np.abs(ref) <= 1.0) & (ref == out)
+    assert np.max(np.abs(out[lo] - ref[lo]), initial=0.0) < 1e-3, (settings, ch, hop)
+    assert np.max(np.abs(out[~lo & ~raw] - ref[~lo & ~raw]), initial=0.0) < 1e-4, (settings, ch, hop)
+
+
+@pytest.mark.gpu
 def test_gpu_wave_requires_all_streams_and_reset():
     from waveform_b200 import WaveEngine, WfError
 
