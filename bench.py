@@ -13,7 +13,7 @@ Besides the contract's keys the line carries:
   parity            the measured launch (same engine geometry, fresh state) against the reference's generic CPU path on a
                     sample of streams: SURVEY.md §8(d) "first 256 frames/shard" + streams from the far ends of the grid
   config.extra      the other layouts of the same 65 536-frame batch (65536x1 ... 256x256) with their roofline fractions, the
-                    other BASELINE.json configs / kernel families (other_shapes: N=4096, 8192, 800, 1920, c1, c2, c4, c5),
+                    other BASELINE.json configs / kernel families (other_shapes: N=4096, 8192, 800, 1920, c1, c2, c4, c5, fused display outputs),
                     a strong-scaling number (65 536 frames TOTAL over the N GPUs) and BASELINE.json configs[4]
                     (N=16384, 128 streams x 256 ticks per GPU, NCCL MAX all-reduce + normalise pass inside the timed loop)
   cpu_baseline      all-cores AVX2 (the value) plus AVX2 on one core and the generic path on one core
