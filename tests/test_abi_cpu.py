@@ -189,3 +189,35 @@ def test_plugin_binding_compiles_against_the_unmodified_reference():
         x = (0.1 * np.random.default_rng(0).standard_normal((1, 8192))).astype(np.float32)
         r = src.run_stft(x, 3, 2048)
         assert (r["db"] == src.db_min).all()      # nothing computed: no device, no fallback
+
+
+def test_zero_weight_taps_equal_the_shortened_kernel_sum():
+    """The display stage (csrc/wf_kernels.cuh, kernel_sum) evaluates interpolation points whose window overlaps the spectrum's
+    edge with ALL taps — weight 0 and a clamped address for the missing ones — instead of the reference's shortened loop
+    (src/filter.hpp:160-169).  The claim that this is the same fp32 sum bit for bit (skipped terms are leading or trailing,
+    x*0 = +-0, the sum starts at +0), restated in numpy float32 with the same sequential mul-then-add order."""
+    rng = np.random.default_rng(5)
+    f32 = np.float32
+    for taps in (4, 8):
+        radius = taps // 2
+        for _ in range(2000):
+            sz = int(rng.integers(taps, 64))
+            db = (-120.0 * rng.uniform(size=sz)).astype(f32)
+            db[rng.uniform(size=sz) < 0.1] = f32(-758.59564)          # DB_MIN entries
+            db[rng.uniform(size=sz) < 0.05] = f32(0.0)
+            w = rng.normal(size=taps).astype(f32)
+            w[rng.uniform(size=taps) < 0.2] = f32(0.0)
+            if rng.uniform() < 0.2:
+                w = -w
+            index = int(rng.integers(0, sz))
+            start = index - radius + 1
+            stop = min(index + radius + 1, sz)
+            ref = f32(0.0)
+            for i in range(max(start, 0), stop):                      # the reference's loop
+                ref = f32(ref + f32(db[i] * w[i - start]))
+            full = f32(0.0)
+            for i in range(taps):                                     # all taps, zero weight + clamped address when out of range
+                j = start + i
+                ok = 0 <= j < sz
+                full = f32(full + f32(db[j if ok else 0] * (w[i] if ok else f32(0.0))))
+            assert ref.tobytes() == full.tobytes(), (taps, sz, index)
