@@ -230,7 +230,19 @@ def test_gpu_wave_chunked_kernel_is_bit_identical_to_the_per_tick_kernel(setting
     including input built to trip the all-zero rule (|x| == 1 -> 0.0 dBFS entries followed by zeros)."""
     from waveform_b200 import WaveEngine
 
-    S, T = 5, 90
+    _chunk_vs_per_tick(settings, ch, hop, 5, 90, monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("settings,ch,hop", [CHUNK_CASES[0], CHUNK_CASES[1], CHUNK_CASES[5]])
+def test_gpu_wave_chunked_kernel_many_streams(settings, ch, hop, monkeypatch):
+    """More streams than resident CTAs (148 SMs x 5): every CTA walks several streams, its shared-memory state is rebuilt per stream."""
+    _chunk_vs_per_tick(settings, ch, hop, 1700, 24, monkeypatch)
+
+
+def _chunk_vs_per_tick(settings, ch, hop, S, T, monkeypatch):
+    from waveform_b200 import WaveEngine
+
     pcm, rms = _case(settings, ch, hop, T, S)
     pcm[1] = 0.0
     pcm[2, :, : 40 * hop] = 1.0          # a buffer full of exactly 0.0 dB ...
